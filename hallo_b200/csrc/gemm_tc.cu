@@ -1,0 +1,432 @@
+// hallo_b200_gemm: persistent warp-specialised tcgen05 GEMM / implicit-GEMM conv3x3.
+//
+//   warp 0      : TMA producer  (A tile 128x64, W tile BNx64 per stage, 128B-swizzled)
+//   warp 1      : MMA issuer    (one elected lane; tcgen05.mma M=128, N=BN, K=16; fp32 in TMEM)
+//   warps 2..5  : epilogue      (tcgen05.ld -> bias / temb / GEGLU / mask / residual -> global)
+//
+// Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of tile i.
+// Tiles are walked n-fastest so the CTAs running concurrently share the same A rows in L2.
+//
+// Implicit conv: the A operand of tap (kh,kw) is the NHWC box shifted by (kh-1, kw-1); TMA's
+// out-of-bounds zero fill supplies the padding, so no im2col buffer exists anywhere.
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace hb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+struct GemmDev {
+  int M, N, K, K1;
+  int tiles_m, tiles_n;
+  void* C;
+  long long ldc;
+  const void* bias;
+  const void* group_bias;
+  long long ld_group_bias;
+  int rows_per_group;
+  const void* row_scale;
+  const void* residual;
+  long long ldr;
+  float alpha;
+  int flags;
+  // conv geometry
+  int cin, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <typename T, int BN, int STAGES, bool CONV>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using SM = GemmSmem<BN, STAGES>;
+  constexpr uint32_t kAccStride = 256;  // TMEM column offset between the two accumulator stages
+  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.K1 < p.K) tma_prefetch_desc(&tmA2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = p.K / kBK;
+  const int cin_blocks = CONV ? p.cin / kBK : 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tm = t / p.tiles_n;
+        const int tn = t - tm * p.tiles_n;
+        int n0 = 0, h0 = 0, w0 = 0;
+        if (CONV) {
+          int per_img = p.tiles_w * p.tiles_h;
+          int nb = tm / per_img;
+          int rem = tm - nb * per_img;
+          int hb_ = rem / p.tiles_w;
+          int wb = rem - hb_ * p.tiles_w;
+          n0 = nb * p.box_n;
+          h0 = hb_ * p.box_h;
+          w0 = wb * p.box_w;
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0x11);
+          uint8_t* sa = smem + stage * SM::kStageBytes;
+          uint8_t* sb = sa + SM::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
+          if (CONV) {
+            int tap = kb / cin_blocks;
+            int cb = kb - tap * cin_blocks;
+            int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
+          } else {
+            int k = kb * kBK;
+            if (k < p.K1)
+              tma_load_2d(sa, &tmA, &full_bar[stage], k, tm * kBM);
+            else
+              tma_load_2d(sa, &tmA2, &full_bar[stage], k - p.K1, tm * kBM);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, tn * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_f16(kBM, BN, Cvt<T>::kFmt, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1, 0x21);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 0x22);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
+          const uint32_t sb = sa + SM::kABytes;
+          const uint64_t adesc = make_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 32 B (16 halfs) along K inside the 128 B swizzle row: +2 in (addr >> 4)
+            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* gbias = reinterpret_cast<const T*>(p.group_bias);
+    const T* rscale = reinterpret_cast<const T*>(p.row_scale);
+    const T* resid = reinterpret_cast<const T*>(p.residual);
+    T* C = reinterpret_cast<T*>(p.C);
+    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tm = t / p.tiles_n;
+      const int tn = t - tm * p.tiles_n;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int r_in_tile = quarter * 32 + lane;
+      long long row;
+      if (CONV) {
+        int per_img = p.tiles_w * p.tiles_h;
+        int nb = tm / per_img;
+        int rem = tm - nb * per_img;
+        int hb_ = rem / p.tiles_w;
+        int wb = rem - hb_ * p.tiles_w;
+        int dn = r_in_tile / (p.box_h * p.box_w);
+        int r2 = r_in_tile - dn * (p.box_h * p.box_w);
+        int dh = r2 / p.box_w;
+        int dw = r2 - dh * p.box_w;
+        row = ((long long)(nb * p.box_n + dn) * p.img_h + (hb_ * p.box_h + dh)) * p.img_w +
+              (wb * p.box_w + dw);
+      } else {
+        row = (long long)tm * kBM + r_in_tile;
+      }
+      const bool row_ok = row < p.M;
+      float rs = p.alpha;
+      if (rscale != nullptr && row_ok) rs *= Cvt<T>::to_f(rscale[row]);
+      const T* gb_row = nullptr;
+      if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
+
+      mbar_wait(&tfull_bar[as], aphase, 0x31);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = tn * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 b4 = *reinterpret_cast<const uint4*>(bias + col0 + j);
+              float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
+                     f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
+              v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+              v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+            }
+          }
+        }
+        if (gb_row != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 b4 = *reinterpret_cast<const uint4*>(gb_row + col0 + j);
+              float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
+                     f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
+              v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+              v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+            }
+          }
+        }
+        if (geglu) {
+          // columns come as (value, gate) pairs; 32 accumulator columns -> 16 outputs
+          const int ocol0 = col0 >> 1;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]) * rs;
+          T* dst = C + row * p.ldc + ocol0;
+          if (resid != nullptr) {
+            const T* rp = resid + row * p.ldr + ocol0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += Cvt<T>::to_f(rp[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            if (col0 + 2 * j < p.N) {
+              uint4 o4;
+              o4.x = Cvt<T>::pack2(o[j + 0], o[j + 1]);
+              o4.y = Cvt<T>::pack2(o[j + 2], o[j + 3]);
+              o4.z = Cvt<T>::pack2(o[j + 4], o[j + 5]);
+              o4.w = Cvt<T>::pack2(o[j + 6], o[j + 7]);
+              *reinterpret_cast<uint4*>(dst + j) = o4;
+            }
+          }
+        } else {
+          T* dst = C + row * p.ldc + col0;
+          const T* rp = resid != nullptr ? resid + row * p.ldr + col0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              float w[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) w[q] = v[j + q] * rs;
+              if (rp != nullptr) {
+                uint4 b4 = *reinterpret_cast<const uint4*>(rp + j);
+                float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
+                       f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
+                w[0] += f0.x; w[1] += f0.y; w[2] += f1.x; w[3] += f1.y;
+                w[4] += f2.x; w[5] += f2.y; w[6] += f3.x; w[7] += f3.y;
+              }
+              uint4 o4;
+              o4.x = Cvt<T>::pack2(w[0], w[1]);
+              o4.y = Cvt<T>::pack2(w[2], w[3]);
+              o4.z = Cvt<T>::pack2(w[4], w[5]);
+              o4.w = Cvt<T>::pack2(w[6], w[7]);
+              *reinterpret_cast<uint4*>(dst + j) = o4;
+            }
+          }
+        }
+        }  // row_ok
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// pick an NHWC box (box_w, box_h, box_n) of 128 pixels that tiles the image batch exactly
+static bool pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
+  for (int cw = 128; cw >= 1; cw >>= 1) {
+    if (w % cw != 0) continue;
+    int rest = 128 / cw;
+    for (int ch = rest; ch >= 1; ch >>= 1) {
+      if (h % ch != 0) continue;
+      int cn = rest / ch;
+      if (n % cn != 0) continue;
+      *bw = cw;
+      *bh = ch;
+      *bn = cn;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <typename T, int BN, int STAGES>
+static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
+  using SM = GemmSmem<BN, STAGES>;
+  GemmDev d{};
+  d.M = q->M;
+  d.N = q->N;
+  d.K = q->K;
+  d.K1 = (q->A2 != nullptr) ? q->K1 : q->K;
+  d.C = q->C;
+  d.ldc = q->ldc;
+  d.bias = q->bias;
+  d.group_bias = q->group_bias;
+  d.ld_group_bias = q->ld_group_bias;
+  d.rows_per_group = q->rows_per_group > 0 ? q->rows_per_group : 1;
+  d.row_scale = q->row_scale;
+  d.residual = q->residual;
+  d.ldr = q->ldr;
+  d.alpha = q->alpha;
+  d.flags = q->flags;
+  d.tiles_n = (q->N + BN - 1) / BN;
+
+  CUtensorMap tmA, tmA2, tmB;
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)q->K, (uint64_t)q->N};
+    uint64_t str[1] = {(uint64_t)q->ldw * 2};
+    uint32_t box[2] = {kBK, (uint32_t)BN};
+    if ((rc = make_tmap_16b(&tmB, q->dtype, q->W, 2, dims, str, box)) != HB_OK) return rc;
+  }
+  if (q->conv3x3) {
+    const int cin = q->K / 9;
+    if (q->K % 9 != 0 || cin % kBK != 0)
+      return fail(HB_ERR_BAD_SHAPE, "conv3x3 needs Cin %% 64 == 0 (K=%d)", q->K);
+    if ((long long)q->img_n * q->img_h * q->img_w != q->M)
+      return fail(HB_ERR_BAD_SHAPE, "conv3x3 M=%d != n*h*w", q->M);
+    int bw, bh, bn;
+    if (!pick_conv_box(q->img_n, q->img_h, q->img_w, &bw, &bh, &bn))
+      return fail(HB_ERR_BAD_SHAPE, "conv3x3: no 128-pixel box tiles %dx%dx%d", q->img_n, q->img_h,
+                  q->img_w);
+    d.cin = cin;
+    d.img_h = q->img_h;
+    d.img_w = q->img_w;
+    d.box_w = bw;
+    d.box_h = bh;
+    d.box_n = bn;
+    d.tiles_w = q->img_w / bw;
+    d.tiles_h = q->img_h / bh;
+    d.tiles_m = d.tiles_w * d.tiles_h * (q->img_n / bn);
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)q->img_w, (uint64_t)q->img_h, (uint64_t)q->img_n};
+    uint64_t str[3] = {(uint64_t)q->lda * 2, (uint64_t)q->lda * 2 * q->img_w,
+                       (uint64_t)q->lda * 2 * q->img_w * q->img_h};
+    uint32_t box[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    if ((rc = make_tmap_16b(&tmA, q->dtype, q->A, 4, dims, str, box)) != HB_OK) return rc;
+    tmA2 = tmA;
+  } else {
+    d.tiles_m = (q->M + kBM - 1) / kBM;
+    uint64_t dims[2] = {(uint64_t)d.K1, (uint64_t)q->M};
+    uint64_t str[1] = {(uint64_t)q->lda * 2};
+    uint32_t box[2] = {kBK, kBM};
+    if ((rc = make_tmap_16b(&tmA, q->dtype, q->A, 2, dims, str, box)) != HB_OK) return rc;
+    if (q->A2 != nullptr) {
+      uint64_t dims2[2] = {(uint64_t)(q->K - q->K1), (uint64_t)q->M};
+      uint64_t str2[1] = {(uint64_t)q->lda2 * 2};
+      if ((rc = make_tmap_16b(&tmA2, q->dtype, q->A2, 2, dims2, str2, box)) != HB_OK) return rc;
+    } else {
+      tmA2 = tmA;
+    }
+  }
+
+  const int tiles = d.tiles_m * d.tiles_n;
+  if (tiles <= 0) return HB_OK;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true> : gemm_tc_kernel<T, BN, STAGES, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[q->conv3x3 ? 1 : 0]) {
+    HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set[q->conv3x3 ? 1 : 0] = true;
+  }
+  kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(tmA, tmA2, tmB, d);
+  HB_LAUNCH_CHECK();
+  return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
+  using namespace hb;
+  if (p == nullptr || p->A == nullptr || p->W == nullptr || p->C == nullptr)
+    return fail(HB_ERR_NULL, "hallo_b200_gemm: null pointer");
+  if (p->M <= 0 || p->N <= 0 || p->K <= 0 || p->K % kBK != 0)
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: M=%d N=%d K=%d (K %% 64 != 0?)", p->M, p->N, p->K);
+  if (p->N % 8 != 0 || p->lda % 8 != 0 || p->ldw % 8 != 0 || p->ldc % 8 != 0 ||
+      (p->residual && p->ldr % 8 != 0) || ((p->flags & HB_EPI_GEGLU) && p->N % 16 != 0))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: leading dims / N must be multiples of 8");
+  if (p->A2 != nullptr && (p->K1 % kBK != 0 || p->K1 <= 0 || p->K1 >= p->K || p->conv3x3))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: bad K split %d of %d", p->K1, p->K);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // 160 divides every channel count of the UNet (320, 640, 1280, ...), so N tiles are never ragged.
+  if (p->dtype == HB_F16) return launch_gemm<__half, 160, 5>(p, s);
+  if (p->dtype == HB_BF16) return launch_gemm<__nv_bfloat16, 160, 5>(p, s);
+  return fail(HB_ERR_BAD_DTYPE, "hallo_b200_gemm: dtype %d", p->dtype);
+}

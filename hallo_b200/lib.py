@@ -1,0 +1,91 @@
+"""ctypes binding of the C-ABI library (include/hallo_b200.h).
+
+The product path has no CPU or PyTorch fallback: if ``libhallo_b200.so`` is missing or a call
+fails, a ``RuntimeError`` is raised (north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhallo_b200.so")
+
+HB_F16, HB_BF16 = 0, 1
+HB_EPI_GEGLU = 1
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("K1", C.c_int32),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("bias", C.c_void_p),
+        ("group_bias", C.c_void_p), ("ld_group_bias", C.c_int64), ("rows_per_group", C.c_int32),
+        ("row_scale", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("alpha", C.c_float),
+        ("flags", C.c_int32),
+        ("conv3x3", C.c_int32),
+        ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "hallo_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.hallo_b200_abi_version.restype = C.c_int
+    lib.hallo_b200_last_error.restype = C.c_char_p
+    lib.hallo_b200_launch_count.restype = C.c_int64
+    lib.hallo_b200_launch_count.argtypes = [C.c_int]
+    lib.hallo_b200_device_error.argtypes = [C.POINTER(C.c_uint)]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().hallo_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"hallo_b200 {what} failed (status {rc}): {msg}")
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.float16:
+        return HB_F16
+    if torch_dtype == torch.bfloat16:
+        return HB_BF16
+    raise RuntimeError(f"hallo_b200 supports fp16/bf16 storage only, got {torch_dtype}")
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().hallo_b200_launch_count(1 if reset else 0))
+
+
+def device_error() -> int:
+    code = C.c_uint(0)
+    load().hallo_b200_device_error(C.byref(code))
+    return int(code.value)
