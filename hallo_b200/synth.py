@@ -1,0 +1,101 @@
+"""Deterministic synthetic weights and inputs for the denoising hot path.
+
+There is no network, so neither SD-1.5 / AnimateDiff / net.pth weights nor real audio/image
+features exist here.  Everything is drawn from seeded CPU generators so that the oracle, the
+golden-fixture script, the parity tests and bench.py all see bit-identical tensors.
+
+Weight init (not torch's default): every tensor gets its own generator seeded from a hash of its
+key, so any subset can be regenerated independently.
+  weights  ~ N(0, 1/fan_in)        (keeps q.k/sqrt(d) ~ N(0,1): softmaxes are not near-uniform)
+  zero_w   ~ N(0, 1/fan_in) * 0.5  (the reference zero-initialises these; de-zeroed so the audio and
+                                    temporal branches are visible to parity)
+  biases   ~ N(0, 0.05);  norm weight ~ 1 + N(0, 0.1);  norm bias ~ N(0, 0.1)
+  pe       = the sinusoid table of motion_module.py:435-445
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict, List, Optional
+
+import torch
+
+from .spec import UNetConfig, param_spec, reader_bank_order, sinusoid_pe
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    h = hashlib.sha256(f"{seed}:{key}".encode()).digest()
+    return torch.Generator(device="cpu").manual_seed(int.from_bytes(h[:7], "little"))
+
+
+def synth_state_dict(cfg: UNetConfig, seed: int = 0, dtype=torch.float32,
+                     only_prefix: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape, kind in param_spec(cfg):
+        if only_prefix is not None and not key.startswith(only_prefix):
+            continue
+        g = _gen(seed, key)
+        if kind == "pe":
+            t = sinusoid_pe(shape[1], shape[2])
+        elif kind in ("w", "zero_w"):
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+            if kind == "zero_w":
+                t = t * 0.5
+        elif kind == "b":
+            t = torch.randn(shape, generator=g) * 0.05
+        elif kind == "norm_w":
+            t = 1.0 + torch.randn(shape, generator=g) * 0.1
+        elif kind == "norm_b":
+            t = torch.randn(shape, generator=g) * 0.1
+        else:
+            raise ValueError(kind)
+        sd[key] = t.to(dtype)
+    return sd
+
+
+def mask_levels(h: int, w: int):
+    """Token counts of the 4 mask scales (image_processor.py:156-180): latent /1,/2,/4,/8."""
+    return [(h // s) * (w // s) for s in (1, 2, 4, 8)]
+
+
+def synth_inputs(cfg: UNetConfig, h: int, w: int, f: int, seed: int = 42, dtype=torch.float32,
+                 timestep: int = 999, motion_scale=(1.0, 1.0, 1.0)) -> dict:
+    """Inputs of UNet3DConditionModel.forward exactly as FaceAnimatePipeline assembles them for CFG
+    (face_animate.py:345-412): batch row 0 = uncond, row 1 = cond."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    nm = cfg.n_motion_frames
+    lat = torch.randn(1, cfg.in_channels, f, h, w, generator=g)
+    sample = torch.cat([lat, lat], 0)                                   # face_animate.py:398
+    ehs = torch.randn(2, 4, cfg.cross_attention_dim, generator=g)       # [uncond tokens, cond tokens]
+    audio_c = torch.randn(1, f, 32, cfg.audio_attention_dim, generator=g)
+    audio = torch.cat([torch.zeros_like(audio_c), audio_c], 0)          # face_animate.py:377-378
+    mcf_c = torch.randn(1, cfg.block_out_channels[0], f, h, w, generator=g) * 0.5
+    mask_cond_fea = torch.cat([torch.zeros_like(mcf_c), mcf_c], 0)      # face_animate.py:343
+    masks = {}
+    for name in ("full", "face", "lip"):
+        lv = []
+        for L in mask_levels(h, w):
+            m = torch.rand(f, L, generator=g)
+            lv.append(torch.cat([m, m], 0))                             # face_animate.py:345-360
+        masks[name] = lv
+    # ReferenceNet bank per spatial block: rows [ref, m1..m_nm | ref, m1..m_nm] (face_animate.py:388-390)
+    banks = {}
+    nblk = len(cfg.block_out_channels)
+    for name, C in reader_bank_order(cfg):
+        if name.startswith("mid_block"):
+            s = 2 ** (nblk - 1)
+        elif name.startswith("down_blocks"):
+            s = 2 ** int(name.split(".")[1])
+        else:
+            s = 2 ** (nblk - 1 - int(name.split(".")[1]))
+        L = (h // s) * (w // s)
+        # the two CFG halves see different ReferenceNet conditioning, so their banks differ in general
+        bank = torch.randn(2 * (1 + nm), L, C, generator=_gen(seed, "bank:" + name))
+        banks[name] = bank.to(torch.float16)                            # update() casts to fp16 (Q4)
+    out = dict(sample=sample.to(dtype), timestep=timestep, encoder_hidden_states=ehs.to(dtype),
+               audio_embedding=audio.to(dtype), mask_cond_fea=mask_cond_fea.to(dtype),
+               full_mask=[m.to(dtype) for m in masks["full"]], face_mask=[m.to(dtype) for m in masks["face"]],
+               lip_mask=[m.to(dtype) for m in masks["lip"]], motion_scale=list(motion_scale), banks=banks)
+    return out

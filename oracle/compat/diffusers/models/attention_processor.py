@@ -1,0 +1,84 @@
+"""Attention + processors restated from diffusers 0.27.2 (models/attention_processor.py)."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class AttnProcessor:
+    """bmm-softmax-bmm processor (training default when xformers is requested)."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, **kw):
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        b, lq, _ = query.shape
+        h = attn.heads
+        d = query.shape[-1] // h
+
+        def split(x):
+            return x.reshape(x.shape[0], x.shape[1], h, d).permute(0, 2, 1, 3)
+
+        q, k, v = split(query), split(key), split(value)
+        probs = torch.softmax((q @ k.transpose(-1, -2)) * attn.scale, dim=-1).to(v.dtype)
+        out = (probs @ v).permute(0, 2, 1, 3).reshape(b, lq, h * d)
+        out = attn.to_out[0](out)
+        out = attn.to_out[1](out)
+        return out / attn.rescale_output_factor
+
+
+class AttnProcessor2_0:
+    """Default inference processor: F.scaled_dot_product_attention, scale d^-0.5, no mask, no dropout."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, **kw):
+        batch_size = hidden_states.shape[0]
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        inner_dim = key.shape[-1]
+        head_dim = inner_dim // attn.heads
+        query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask,
+                                                       dropout_p=0.0, is_causal=False)
+        hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim)
+        hidden_states = hidden_states.to(query.dtype)
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        return hidden_states / attn.rescale_output_factor
+
+
+AttentionProcessor = object  # typing alias in the reference
+
+
+class Attention(nn.Module):
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
+                 upcast_attention=False, upcast_softmax=False, out_bias=True, scale_qk=True,
+                 only_cross_attention=False, rescale_output_factor=1.0, residual_connection=False,
+                 processor=None, **unused):
+        super().__init__()
+        self.inner_dim = dim_head * heads
+        self.cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.upcast_attention = upcast_attention
+        self.rescale_output_factor = rescale_output_factor
+        self.residual_connection = residual_connection
+        self.scale = dim_head ** -0.5 if scale_qk else 1.0
+        self.heads = heads
+        self.only_cross_attention = only_cross_attention
+        self.to_q = nn.Linear(query_dim, self.inner_dim, bias=bias)
+        self.to_k = nn.Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
+        self.to_v = nn.Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(self.inner_dim, query_dim, bias=out_bias), nn.Dropout(dropout)])
+        self.set_processor(processor if processor is not None else AttnProcessor2_0())
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
+        # 0.27.2 drops kwargs the processor does not name (e.g. video_length) with a warning
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask)

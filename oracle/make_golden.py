@@ -1,0 +1,76 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (through oracle/compat) in THIS container.
+
+    python oracle/make_golden.py
+
+Fixtures (small, committed):
+  unet3d_state_dict_keys.json     key -> shape of the reference UNet3D (1946 entries)  [SURVEY.md 8b]
+  unet_fwd_h{H}_f{F}.pt           reference UNet3D forward output on hallo_b200.synth inputs/weights
+                                  (fp32, shipped branch, read-mode reader with synthetic fp16 banks)
+                                  + per-block output statistics + input checksums
+The weights/inputs are NOT stored: they are regenerated from seeds by hallo_b200/synth.py; the stored
+checksums detect generator drift.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from hallo_b200.spec import UNetConfig  # noqa: E402
+from hallo_b200.synth import synth_inputs, synth_state_dict  # noqa: E402
+from oracle import ref_host  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = [dict(h=8, f=2, seed=42, t=999, ms=(1.0, 0.9, 1.1)),
+         dict(h=16, f=3, seed=43, t=499, ms=(1.0, 1.0, 1.0)),
+         dict(h=16, f=16, seed=44, t=24, ms=(1.2, 0.8, 1.0))]
+
+
+def checksum(t: torch.Tensor) -> float:
+    return float(t.double().abs().sum())
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 8)
+    os.makedirs(GOLD, exist_ok=True)
+    cfg = UNetConfig()
+    unet = ref_host.build_reference_unet()
+    keys = {k: list(v.shape) for k, v in unet.state_dict().items()}
+    with open(os.path.join(GOLD, "unet3d_state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+    sd = synth_state_dict(cfg, seed=0)
+    unet.load_state_dict(sd, strict=True)
+    wsum = {k: checksum(sd[k]) for k in ("conv_in.weight", "mid_block.attentions.0.transformer_blocks.0.attn1.to_q.weight",
+                                          "up_blocks.3.motion_modules.2.temporal_transformer.proj_out.weight")}
+    for c in CASES:
+        inp = synth_inputs(cfg, c["h"], c["h"], c["f"], seed=c["seed"], timestep=c["t"], motion_scale=c["ms"])
+        ref_host.attach_reader(unet, inp["banks"])
+        taps = {}
+        hooks = []
+        for name in ["down_blocks.0", "down_blocks.1", "down_blocks.2", "down_blocks.3", "mid_block",
+                     "up_blocks.0", "up_blocks.1", "up_blocks.2", "up_blocks.3"]:
+            mod = unet.get_submodule(name)
+
+            def mk(n):
+                def hook(m, i, o):
+                    t = o[0] if isinstance(o, tuple) else o
+                    taps[n] = dict(mean=float(t.mean()), std=float(t.std()), abs_sum=checksum(t))
+                return hook
+            hooks.append(mod.register_forward_hook(mk(name)))
+        out = ref_host.run_reference_unet(unet, inp)
+        for hk in hooks:
+            hk.remove()
+        fx = dict(case=c, out=out.clone(), taps=taps, weight_checksums=wsum,
+                  input_checksums=dict(sample=checksum(inp["sample"]), audio=checksum(inp["audio_embedding"]),
+                                       bank0=checksum(inp["banks"]["mid_block.attentions.0"].float())),
+                  torch_version=torch.__version__)
+        path = os.path.join(GOLD, f"unet_fwd_h{c['h']}_f{c['f']}.pt")
+        torch.save(fx, path)
+        print("wrote", path, tuple(out.shape), "std", float(out.std()))
+
+
+if __name__ == "__main__":
+    main()
