@@ -33,7 +33,7 @@ struct GemmDev {
   float alpha;
   int flags;
   // conv geometry
-  int cin, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h;
+  int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
 
 template <int BN, int STAGES>
@@ -119,7 +119,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int tap = kb / cin_blocks;
             int cb = kb - tap * cin_blocks;
             int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
+            if (p.stride2) {
+              // input is stored as 4 phase planes [(p*2+q)*img_n + n][h/2][w/2][C] (x[2i+p][2j+q]);
+              // tap kh reads phase (kh==1 ? 0 : 1) at row offset (kh==0 ? -1 : 0)
+              const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
+              tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 - (kw == 0), h0 - (kh == 0),
+                          (ph * 2 + pw) * p.img_n + n0);
+            } else {
+              tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
+            }
           } else {
             int k = kb * kBK;
             if (k < p.K1)
@@ -246,6 +254,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (p.flags & HB_EPI_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        }
         if (geglu) {
           // columns come as (value, gate) pairs; 32 accumulator columns -> 16 outputs
           const int ocol0 = col0 >> 1;
@@ -368,6 +380,8 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
       return fail(HB_ERR_BAD_SHAPE, "conv3x3: no 128-pixel box tiles %dx%dx%d", q->img_n, q->img_h,
                   q->img_w);
     d.cin = cin;
+    d.img_n = q->img_n;
+    d.stride2 = q->conv3x3 == 2 ? 1 : 0;
     d.img_h = q->img_h;
     d.img_w = q->img_w;
     d.box_w = bw;
@@ -376,7 +390,8 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
     d.tiles_w = q->img_w / bw;
     d.tiles_h = q->img_h / bh;
     d.tiles_m = d.tiles_w * d.tiles_h * (q->img_n / bn);
-    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)q->img_w, (uint64_t)q->img_h, (uint64_t)q->img_n};
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)q->img_w, (uint64_t)q->img_h,
+                        (uint64_t)q->img_n * (q->conv3x3 == 2 ? 4 : 1)};
     uint64_t str[3] = {(uint64_t)q->lda * 2, (uint64_t)q->lda * 2 * q->img_w,
                        (uint64_t)q->lda * 2 * q->img_w * q->img_h};
     uint32_t box[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};

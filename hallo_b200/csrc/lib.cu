@@ -2,6 +2,8 @@
 // the launch counter have exactly one definition (no -rdc needed).
 #include "host_common.cu"
 #include "gemm_tc.cu"
+#include "attn_tc.cu"
+#include "aux.cu"
 
 extern "C" int hallo_b200_device_error(unsigned int* code_out) {
   unsigned int v = 0;

@@ -1,0 +1,614 @@
+"""Kernel-plan executor for the denoising UNet3D (the device hot path).
+
+The reference walks an nn.Module tree and issues ~2.3k library kernels per forward
+(hallo/models/unet_3d.py:510-715 and everything below it).  Here the same arithmetic is a flat,
+pre-planned sequence of hand-written sm_100a kernels (hallo_b200/csrc) over channels-last token
+matrices, with all weights pre-packed once and all step-invariant work hoisted out of the 40-step loop:
+
+  per model load : weight packing (fused QKV, interleaved GEGLU, [Cout][tap][Cin] convs, ...)
+  per window     : ReferenceNet-bank K/V, image-token K/V, audio-token K/V, motion-frame GroupNorm
+                   inputs, masks, mask_cond_fea, motion_scale-folded zero-conv weights
+  per step       : the kernels in `_forward()` -- captured once into a CUDA graph and replayed.
+
+Layout: every activation is a token matrix [rows, C]; rows are ordered (cfg_half, frame, pixel) --
+i.e. the reference's `(b f) (h w) c` -- so NCHW<->NLC permutes, `rearrange`s and `torch.cat`s of the
+reference disappear (channel concats become two-source reads, frame concats become row offsets).
+
+Multi-GPU: a rank owns `halves` x `frames` (a CFG half and a contiguous frame shard); the only
+exchange on the path is the all-gather of temporal-attention K/V inside a CFG group, plus a tiny
+all-gather of the model output for the CFG combine.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .spec import BlockSpec, LayerSpec, ResnetSpec, UNetConfig, build_blocks, reader_bank_order
+
+
+@dataclass
+class Shard:
+    """Which (cfg half, frame) rows this rank owns.  halves: subset of (0, 1); frames: global frame ids."""
+    halves: Tuple[int, ...] = (0, 1)
+    frames: Tuple[int, ...] = tuple(range(16))
+    group: Optional[object] = None          # torch.distributed group of the ranks sharing a CFG half
+    group_size: int = 1
+    world: Optional[object] = None          # group for the CFG-combine exchange
+    world_size: int = 1
+    rank_in_group: int = 0
+
+
+class PackedWeights:
+    """Device-resident, kernel-ready copies of the state dict (packed once per model load)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: UNetConfig, device, dtype):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+        blocks = build_blocks(cfg)
+        self.blocks = blocks
+
+        def dev(x):
+            return x.detach().to(device=device, dtype=dtype).contiguous()
+
+        def put(name, x):
+            self.t[name] = dev(x)
+
+        def lin(name, bias=True):
+            put(f"{name}.w", sd[f"{name}.weight"].reshape(sd[f"{name}.weight"].shape[0], -1))
+            if bias and f"{name}.bias" in sd:
+                put(f"{name}.b", sd[f"{name}.bias"])
+
+        def norm(name):
+            put(f"{name}.w", sd[f"{name}.weight"])
+            put(f"{name}.b", sd[f"{name}.bias"])
+
+        def conv3(name):
+            put(f"{name}.w", ops.pack_conv3x3_weight(sd[f"{name}.weight"]))
+            put(f"{name}.b", sd[f"{name}.bias"])
+
+        def qkv(name, out_name):
+            put(out_name, torch.cat([sd[f"{name}.to_q.weight"], sd[f"{name}.to_k.weight"], sd[f"{name}.to_v.weight"]], 0))
+
+        def ff(name):
+            wi, bi = ops.pack_geglu_weight(sd[f"{name}.net.0.proj.weight"], sd[f"{name}.net.0.proj.bias"])
+            put(f"{name}.w1", wi)
+            put(f"{name}.b1", bi)
+            lin(f"{name}.net.2")
+
+        # stem / head
+        w_in = sd["conv_in.weight"]                                  # [C0, Cl, 3, 3] -> [C0, 64], k = tap*Cl + c
+        c0, cl = w_in.shape[0], w_in.shape[1]
+        wi = torch.zeros(c0, 64, dtype=w_in.dtype)
+        wi[:, :9 * cl] = w_in.permute(0, 2, 3, 1).reshape(c0, 9 * cl)
+        put("conv_in.w", wi)
+        put("conv_in.b", sd["conv_in.bias"])
+        lin("time_embedding.linear_1")
+        lin("time_embedding.linear_2")
+        norm("conv_norm_out")
+        w_out = ops.pack_conv3x3_weight(sd["conv_out.weight"])       # [Cl, 9*C0] -> padded to 8 rows
+        wo = torch.zeros(8, w_out.shape[1], dtype=w_out.dtype)
+        wo[:w_out.shape[0]] = w_out
+        bo = torch.zeros(8, dtype=w_out.dtype)
+        bo[:w_out.shape[0]] = sd["conv_out.bias"]
+        put("conv_out.w", wo)
+        put("conv_out.b", bo)
+
+        temb_w, temb_b = [], []
+        self.temb_off: Dict[str, int] = {}
+        off = 0
+
+        def resnet(rs: ResnetSpec):
+            nonlocal off
+            norm(f"{rs.name}.norm1")
+            conv3(f"{rs.name}.conv1")
+            norm(f"{rs.name}.norm2")
+            conv3(f"{rs.name}.conv2")
+            if rs.has_shortcut:
+                lin(f"{rs.name}.conv_shortcut")
+            temb_w.append(sd[f"{rs.name}.time_emb_proj.weight"])
+            temb_b.append(sd[f"{rs.name}.time_emb_proj.bias"])
+            self.temb_off[rs.name] = off
+            off += rs.cout
+
+        for b in blocks:
+            if b.extra_resnet is not None:
+                resnet(b.extra_resnet)
+            for l in b.layers:
+                resnet(l.resnet)
+                if l.attn:
+                    n = l.attn
+                    tb = f"{n}.transformer_blocks.0"
+                    norm(f"{n}.norm"); lin(f"{n}.proj_in"); lin(f"{n}.proj_out")
+                    for k in ("norm1", "norm2", "norm3"):
+                        norm(f"{tb}.{k}")
+                    qkv(f"{tb}.attn1", f"{tb}.attn1.qkv")
+                    put(f"{tb}.attn1.kv", torch.cat([sd[f"{tb}.attn1.to_k.weight"], sd[f"{tb}.attn1.to_v.weight"]], 0))
+                    lin(f"{tb}.attn1.to_out.0")
+                    put(f"{tb}.attn2.q", sd[f"{tb}.attn2.to_q.weight"])
+                    put(f"{tb}.attn2.kv", torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], 0))
+                    lin(f"{tb}.attn2.to_out.0")
+                    ff(f"{tb}.ff")
+                if l.audio:
+                    n = l.audio
+                    tb = f"{n}.transformer_blocks.0"
+                    norm(f"{n}.norm"); lin(f"{n}.proj_in"); lin(f"{n}.proj_out")
+                    for k in ("norm1", "norm2", "norm3"):
+                        norm(f"{tb}.{k}")
+                    qkv(f"{tb}.attn1", f"{tb}.attn1.qkv")
+                    lin(f"{tb}.attn1.to_out.0")
+                    put(f"{tb}.attn2.q3", torch.cat([sd[f"{tb}.attn2_{r}.to_q.weight"] for r in range(3)], 0))
+                    put(f"{tb}.attn2.kv6", torch.cat([torch.cat([sd[f"{tb}.attn2_{r}.to_k.weight"],
+                                                                 sd[f"{tb}.attn2_{r}.to_v.weight"]], 0)
+                                                      for r in range(3)], 0))
+                    for r in range(3):
+                        lin(f"{tb}.attn2_{r}.to_out.0")
+                    # zero convs stay in fp32 on the host side of the pack: folded with motion_scale per window
+                    self.t[f"{tb}.zero.w"] = torch.stack(
+                        [sd[f"{tb}.zero_conv_{r}.weight"].reshape(l.audio_inner, l.audio_inner).float()
+                         for r in ("full", "face", "lip")], 0).to(device)
+                    self.t[f"{tb}.zero.b"] = torch.stack([sd[f"{tb}.zero_conv_{r}.bias"].float()
+                                                          for r in ("full", "face", "lip")], 0).to(device)
+                    ff(f"{tb}.ff")
+                if l.motion and l.motion_executed:
+                    tt = f"{l.motion}.temporal_transformer"
+                    tb = f"{tt}.transformer_blocks.0"
+                    norm(f"{tt}.norm"); lin(f"{tt}.proj_in"); lin(f"{tt}.proj_out")
+                    for a in range(2):
+                        norm(f"{tb}.norms.{a}")
+                        qkv(f"{tb}.attention_blocks.{a}", f"{tb}.attention_blocks.{a}.qkv")
+                        lin(f"{tb}.attention_blocks.{a}.to_out.0")
+                        self.t[f"{tb}.attention_blocks.{a}.pe"] = \
+                            sd[f"{tb}.attention_blocks.{a}.pos_encoder.pe"][0].float().to(device).contiguous()
+                    norm(f"{tb}.ff_norm")
+                    ff(f"{tb}.ff")
+            if b.downsampler:
+                conv3(f"{b.downsampler}.conv")
+            if b.upsampler:
+                conv3(f"{b.upsampler}.conv")
+        put("temb_all.w", torch.cat(temb_w, 0))
+        put("temb_all.b", torch.cat(temb_b, 0))
+        self.temb_total = off
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+    def get(self, k):
+        return self.t.get(k)
+
+
+class DenoiseEngine:
+    """Executes UNet3D forward (+ optional CFG/DDIM step) for one rank's shard of a window."""
+
+    def __init__(self, weights: PackedWeights, h: int, w: int, n_frames: int, shard: Optional[Shard] = None):
+        self.W = weights
+        self.cfg = weights.cfg
+        self.dtype = weights.dtype
+        self.dev = weights.device
+        self.h, self.w, self.f = h, w, n_frames
+        self.shard = shard or Shard(frames=tuple(range(n_frames)))
+        self.nb = len(self.shard.halves)
+        self.fl = len(self.shard.frames)
+        self.nm = self.cfg.n_motion_frames
+        self.B = self.nb * self.fl                      # local (cfg half, frame) rows
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self.window: Dict[str, torch.Tensor] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        nblk = len(self.cfg.block_out_channels)
+        self.level_hw = [(h >> i, w >> i) for i in range(nblk)]
+        # scheduler state on the device
+        self.step_idx = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.t_table = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.coef = torch.zeros(1, 4, dtype=torch.float32, device=self.dev)
+        self.n_steps = 1
+        self.guidance = 1.0
+        self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
+        self.model_out: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, tag: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
+        key = (tag, rows, cols, dtype or self.dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(rows, cols, device=self.dev, dtype=dtype or self.dtype)
+            self._bufs[key] = t
+        return t
+
+    def L(self, level: int) -> int:
+        hh, ww = self.level_hw[level]
+        return hh * ww
+
+    # ------------------------------------------------------------------ per-window constants
+    def _block_level(self, name: str) -> int:
+        nblk = len(self.cfg.block_out_channels)
+        if name.startswith("mid_block"):
+            return nblk - 1
+        i = int(name.split(".")[1])
+        return i if name.startswith("down_blocks") else nblk - 1 - i
+
+    @torch.no_grad()
+    def begin_window(self, *, encoder_hidden_states, audio_embedding, mask_cond_fea, full_mask, face_mask, lip_mask,
+                     motion_scale, banks: Dict[str, torch.Tensor]):
+        """Hoists everything that does not depend on (latents, timestep) -- SURVEY.md 8a "step-invariant work".
+        Inputs use the reference's shapes (full CFG batch, all frames); this rank slices its shard."""
+        W, cfg, sh = self.W, self.cfg, self.shard
+        dt, dev = self.dtype, self.dev
+        halves, frames = list(sh.halves), list(sh.frames)
+        f, fl, nb, nm, H = self.f, self.fl, self.nb, self.nm, cfg.heads
+        win = self.window
+        fr_idx = torch.tensor(frames, device=dev)
+        # global (b f) row ids of the local rows, in local order
+        rows = [b * f + g for b in halves for g in frames]
+        win["row_ids"] = rows
+        # reference tiles CFG halves over the batch (Q9): row n attends to ref[n % 2]; uncond rows: none (Q3)
+        ridx = [(-1 if n < f else (n % 2)) for n in rows]
+        win["ref_index"] = torch.tensor(ridx, dtype=torch.int32, device=dev)
+        # temporal positions: motion frames 0..nm-1, then nm + global frame id
+        win["pe_index"] = torch.tensor(list(range(nm)) + [nm + g for g in frames], dtype=torch.int32, device=dev)
+
+        ehs = encoder_hidden_states.to(dev, dt)[halves]                       # [nb, 4, 768]
+        aud = audio_embedding.to(dev, dt)[halves][:, fr_idx]                  # [nb, fl, 32, 768]
+        aud2 = aud.reshape(nb * fl * aud.shape[2], aud.shape[3]).contiguous()
+        ehs2 = ehs.reshape(nb * ehs.shape[1], ehs.shape[2]).contiguous()
+        win["n_img_tokens"] = ehs.shape[1]
+        win["n_aud_tokens"] = aud.shape[2]
+        mcf = mask_cond_fea.to(dev, dt)[halves][:, :, fr_idx]                 # [nb, C0, fl, h, w]
+        win["mask_cond"] = mcf.permute(0, 2, 3, 4, 1).reshape(-1, mcf.shape[1]).contiguous()
+        rid = torch.tensor(rows, device=dev)
+        for nme, m in (("full", full_mask), ("face", face_mask), ("lip", lip_mask)):
+            for lv, t in enumerate(m):
+                win[f"mask.{nme}.{lv}"] = t.to(dev, dt)[rid].reshape(-1).contiguous()
+        ms = [float(x) for x in motion_scale] if motion_scale is not None else [1.0, 1.0, 1.0]
+
+        for b in W.blocks:
+            lv = self._block_level(b.name)
+            L = self.L(lv)
+            for l in b.layers:
+                if l.attn:
+                    tb = f"{l.attn}.transformer_blocks.0"
+                    C = b.channels
+                    bank = banks[l.attn].to(dev, torch.float16).to(dt)          # update() casts to fp16 (Q4)
+                    bank = bank.reshape(2, 1 + nm, L, C)
+                    refs = bank[:, 0].reshape(2 * L, C).contiguous()           # both CFG halves' ref tokens
+                    kv = torch.empty(2 * L, 2 * C, device=dev, dtype=dt)
+                    ops.gemm(refs, W[f"{tb}.attn1.kv"], kv)
+                    win[f"{l.attn}.kvref"] = kv
+                    kvi = torch.empty(ehs2.shape[0], 2 * C, device=dev, dtype=dt)
+                    ops.gemm(ehs2, W[f"{tb}.attn2.kv"], kvi)
+                    win[f"{l.attn}.kvimg"] = kvi
+                    # motion-frame features of the local halves, token layout [nb*nm*L, C]
+                    win[f"{l.attn}.motion"] = bank[halves][:, 1:].reshape(nb * nm * L, C).contiguous()
+                if l.audio:
+                    tb = f"{l.audio}.transformer_blocks.0"
+                    Ci = l.audio_inner
+                    kva = torch.empty(aud2.shape[0], 6 * Ci, device=dev, dtype=dt)
+                    ops.gemm(aud2, W[f"{tb}.attn2.kv6"], kva)
+                    win[f"{l.audio}.kvaud"] = kva
+                    zw, zb = W[f"{tb}.zero.w"], W[f"{tb}.zero.b"]
+                    win[f"{l.audio}.zero.w"] = torch.cat([ms[r] * zw[r] for r in range(3)], 1).to(dt).contiguous()
+                    win[f"{l.audio}.zero.b"] = sum(ms[r] * zb[r] for r in range(3)).to(dt).contiguous()
+                if l.motion and l.motion_executed:
+                    # GroupNorm of the motion frames is step-invariant: normalise once into frames [0, nm)
+                    tt = f"{l.motion}.temporal_transformer"
+                    C = b.channels
+                    gn18 = self.buf(f"{l.motion}.gn18", nb * (nm + fl) * L, C)
+                    ws = self.buf("gn_ws", 1, 2 * 64 * 64, torch.float32)
+                    ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
+                                  n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
+                                  fpb_in=nm, fpb_out=nm + fl, frame_off=0)
+        torch.cuda.current_stream().synchronize()
+
+    def set_schedule(self, timesteps: Sequence[int], coef: torch.Tensor, guidance: float):
+        self.n_steps = len(timesteps)
+        self.t_table = torch.tensor([float(t) for t in timesteps], dtype=torch.float32, device=self.dev)
+        self.coef = coef.to(self.dev, torch.float32).contiguous()
+        self.guidance = float(guidance)
+        self.step_idx.zero_()
+
+    # ------------------------------------------------------------------ modules
+    def _gn(self, x1, name, out, n_frames, hw, eps, silu, x2=None, **kw):
+        ws = self.buf("gn_ws", 1, 2 * 64 * 64, torch.float32)
+        return ops.groupnorm(x1, self.W[f"{name}.w"], self.W[f"{name}.b"], out, ws, n_frames=n_frames, hw=hw,
+                             groups=self.cfg.norm_num_groups, eps=eps, silu=silu, x2=x2, **kw)
+
+    def _ln(self, x, name, tag, **kw):
+        out = self.buf(tag, x.shape[0], x.shape[1])
+        return ops.layernorm(x, self.W[f"{name}.w"], self.W[f"{name}.b"], out, **kw)
+
+    def _resnet(self, rs: ResnetSpec, x1, x2, level: int, out_tag: str):
+        W, B = self.W, self.B
+        hh, ww = self.level_hw[level]
+        L = hh * ww
+        M = B * L
+        cin, cout = rs.cin, rs.cout
+        t1 = self.buf("rs.gn1", M, cin)
+        self._gn(x1, f"{rs.name}.norm1", t1, B, L, self.cfg.norm_eps, True, x2=x2)
+        t2 = self.buf("rs.c1", M, cout)
+        off = W.temb_off[rs.name]
+        ops.conv3x3(t1.view(B, hh, ww, cin), W[f"{rs.name}.conv1.w"], t2, bias=W[f"{rs.name}.conv1.b"],
+                    group_bias=self.temb_all[:, off:off + cout], rows_per_group=self.fl * L)
+        t3 = self.buf("rs.gn2", M, cout)
+        self._gn(t2, f"{rs.name}.norm2", t3, B, L, self.cfg.norm_eps, True)
+        if rs.has_shortcut:
+            sc = self.buf("rs.sc", M, cout)
+            ops.gemm(x1, W[f"{rs.name}.conv_shortcut.w"], sc, bias=W[f"{rs.name}.conv_shortcut.b"], a2=x2)
+        else:
+            assert x2 is None
+            sc = x1
+        out = self.buf(out_tag, M, cout)
+        ops.conv3x3(t3.view(B, hh, ww, cout), W[f"{rs.name}.conv2.w"], out, bias=W[f"{rs.name}.conv2.b"], residual=sc)
+        return out
+
+    def _ff(self, x, name, norm_name, tag):
+        W = self.W
+        n = self._ln(x, norm_name, "ln")
+        M, C = x.shape
+        g = self.buf("ff.mid", M, 4 * C)
+        ops.gemm(n, W[f"{name}.w1"], g, bias=W[f"{name}.b1"], geglu=True)
+        out = self.buf(tag, M, C)
+        ops.gemm(g, W[f"{name}.net.2.w"], out, bias=W[f"{name}.net.2.b"], residual=x)
+        return out
+
+    def _spatial(self, name: str, x, level: int, C: int, out_tag: str):
+        W, B, win, H = self.W, self.B, self.window, self.cfg.heads
+        L = self.L(level)
+        M = B * L
+        tb = f"{name}.transformer_blocks.0"
+        t = self.buf("tf.gn", M, C)
+        self._gn(x, f"{name}.norm", t, B, L, 1e-6, False)
+        h = self.buf("tf.h0", M, C)
+        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"])
+        n1 = self._ln(h, f"{tb}.norm1", "ln")
+        qkv = self.buf("tf.qkv", M, 3 * C)
+        ops.gemm(n1, W[f"{tb}.attn1.qkv"], qkv)
+        a = self.buf("tf.attn", M, C)
+        kvref = win[f"{name}.kvref"]
+        ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], a, heads=H, L=L, kref=kvref[:, :C], vref=kvref[:, C:],
+                      ref_index=win["ref_index"])
+        h1 = self.buf("tf.h1", M, C)
+        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h)
+        n2 = self._ln(h1, f"{tb}.norm2", "ln")
+        q2 = self.buf("tf.q2", M, C)
+        ops.gemm(n2, W[f"{tb}.attn2.q"], q2)
+        kvi = win[f"{name}.kvimg"]
+        a2 = self.buf("tf.attn", M, C)
+        ops.cross_attention(q2, kvi[:, :C], kvi[:, C:], a2, frames=B, tokens=L, heads=H, head_dim=C // H,
+                            n_keys=win["n_img_tokens"], kv_frame_div=self.fl)
+        h2 = self.buf("tf.h2", M, C)
+        ops.gemm(a2, W[f"{tb}.attn2.to_out.0.w"], h2, bias=W[f"{tb}.attn2.to_out.0.b"], residual=h1)
+        h3 = self._ff(h2, f"{tb}.ff", f"{tb}.norm3", "tf.h3")
+        out = self.buf(out_tag, M, C)
+        ops.gemm(h3, W[f"{name}.proj_out.w"], out, bias=W[f"{name}.proj_out.b"], residual=x)
+        return out
+
+    def _audio(self, name: str, x, level: int, C: int, Ci: int, depth: int, out_tag: str):
+        W, B, win, H = self.W, self.B, self.window, self.cfg.heads
+        L = self.L(level)
+        M = B * L
+        tb = f"{name}.transformer_blocks.0"
+        t = self.buf("tf.gn", M, C)
+        self._gn(x, f"{name}.norm", t, B, L, 1e-6, False)
+        h = self.buf("au.h0", M, Ci)
+        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"])
+        n1 = self._ln(h, f"{tb}.norm1", "ln")
+        qkv = self.buf("tf.qkv", M, 3 * Ci)
+        ops.gemm(n1, W[f"{tb}.attn1.qkv"], qkv)
+        a = self.buf("tf.attn", M, Ci)
+        ops.attention(qkv[:, :Ci], qkv[:, Ci:2 * Ci], qkv[:, 2 * Ci:], a, heads=H, L=L)
+        h1 = self.buf("au.h1", M, Ci)
+        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h)
+        n2 = self._ln(h1, f"{tb}.norm2", "ln")
+        q3 = self.buf("au.q3", M, 3 * Ci)
+        ops.gemm(n2, W[f"{tb}.attn2.q3"], q3)
+        kva = win[f"{name}.kvaud"]
+        a3 = self.buf("au.a3", M, 3 * Ci)
+        ops.cross_attention(q3, kva[:, :Ci], kva[:, Ci:2 * Ci], a3, frames=B, tokens=L, heads=H, head_dim=Ci // H,
+                            n_keys=win["n_aud_tokens"], kv_frame_div=1, regions=3, q_region_stride=Ci,
+                            kv_region_stride=2 * Ci, o_region_stride=Ci)
+        m3 = self.buf("au.m3", M, 3 * Ci)
+        for r, rn in enumerate(("full", "face", "lip")):
+            ops.gemm(a3[:, r * Ci:(r + 1) * Ci], W[f"{tb}.attn2_{r}.to_out.0.w"], m3[:, r * Ci:(r + 1) * Ci],
+                     bias=W[f"{tb}.attn2_{r}.to_out.0.b"], row_scale=win[f"mask.{rn}.{depth}"])
+        h2 = self.buf("au.h2", M, Ci)
+        ops.gemm(m3, win[f"{name}.zero.w"], h2, bias=win[f"{name}.zero.b"], residual=h1)
+        h3 = self._ff(h2, f"{tb}.ff", f"{tb}.norm3", "au.h3")
+        out = self.buf(out_tag, M, C)
+        ops.gemm(h3, W[f"{name}.proj_out.w"], out, bias=W[f"{name}.proj_out.b"], residual=x)
+        return out
+
+    def _gather_kv(self, qkv, C, L):
+        """Temporal K/V of all frames of this CFG half.  Single rank per half: a view.  Sharded: the one
+        NCCL all-gather on the path -- motion-frame rows are replicated, so only the local
+        frames' K/V are exchanged."""
+        sh = self.shard
+        nb, nm, fl = self.nb, self.nm, self.fl
+        Fl = nm + fl
+        if sh.group_size == 1:
+            return qkv[:, C:2 * C], qkv[:, 2 * C:], Fl
+        import torch.distributed as dist
+        assert nb == 1
+        Fk = nm + fl * sh.group_size
+        loc = qkv.view(Fl, L, 3 * C)[nm:, :, C:].contiguous()                     # [fl, L, 2C]
+        full = self.buf("mm.kvfull", Fk * L, 2 * C)
+        full.view(Fk, L, 2 * C)[:nm].copy_(qkv.view(Fl, L, 3 * C)[:nm, :, C:])
+        dist.all_gather_into_tensor(full.view(Fk, L, 2 * C)[nm:].reshape(-1), loc.reshape(-1), group=sh.group)
+        return full[:, :C], full[:, C:], Fk
+
+    def _motion(self, name: str, attn_name: str, x, level: int, C: int, out_tag: str):
+        W, win, H = self.W, self.window, self.cfg.heads
+        nb, nm, fl = self.nb, self.nm, self.fl
+        Fl = nm + fl
+        L = self.L(level)
+        Mm = nb * Fl * L
+        tt = f"{name}.temporal_transformer"
+        tb = f"{tt}.transformer_blocks.0"
+        gn18 = self.buf(f"{name}.gn18", Mm, C)          # frames [0, nm) were filled in begin_window
+        self._gn(x, f"{tt}.norm", gn18, nb * fl, L, 1e-6, False, fpb_in=fl, fpb_out=Fl, frame_off=nm)
+        h = self.buf("mm.h", Mm, C)
+        ops.gemm(gn18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"])
+        for a in range(2):
+            n = self._ln(h, f"{tb}.norms.{a}", "mm.ln", pe=W[f"{tb}.attention_blocks.{a}.pe"], pe_index=win["pe_index"],
+                         tokens_per_frame=L, frames=Fl)
+            qkv = self.buf("mm.qkv", Mm, 3 * C)
+            ops.gemm(n, W[f"{tb}.attention_blocks.{a}.qkv"], qkv)
+            k, v, Fk = self._gather_kv(qkv, C, L)
+            o = self.buf("mm.attn", Mm, C)
+            ops.temporal_attention(qkv[:, :C], k, v, o, batch=nb, fq=Fl, fk=Fk, tokens=L, heads=H)
+            h2 = self.buf(f"mm.h{a + 1}", Mm, C)
+            ops.gemm(o, W[f"{tb}.attention_blocks.{a}.to_out.0.w"], h2,
+                     bias=W[f"{tb}.attention_blocks.{a}.to_out.0.b"], residual=h)
+            h = h2
+        h = self._ff(h, f"{tb}.ff", f"{tb}.ff_norm", "mm.h3")
+        out = self.buf(out_tag, nb * fl * L, C)
+        for b in range(nb):                              # proj_out only on the real frames (drops motion frames)
+            rows_in = slice((b * Fl + nm) * L, (b + 1) * Fl * L)
+            rows_out = slice(b * fl * L, (b + 1) * fl * L)
+            ops.gemm(h[rows_in], W[f"{tt}.proj_out.w"], out[rows_out], bias=W[f"{tt}.proj_out.b"], residual=x[rows_out])
+        return out
+
+    def _cross_layer(self, b: BlockSpec, l: LayerSpec, x1, x2, level: int, out_tag: str):
+        C = b.channels
+        x = self._resnet(l.resnet, x1, x2, level, "lyr.rs")
+        x = self._spatial(l.attn, x, level, C, "lyr.sp")
+        x = self._audio(l.audio, x, level, C, l.audio_inner, b.depth, "lyr.au")
+        return self._motion(l.motion, l.attn, x, level, C, out_tag)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def _forward(self):
+        """One UNet3D forward over the local shard; reads self.latents, writes self.model_out [B*L0, 8]."""
+        W, cfg, B = self.W, self.cfg, self.B
+        h, w = self.h, self.w
+        L0 = h * w
+        c0 = cfg.block_out_channels[0]
+        # time embedding (unet_3d.py:565-588) -> SiLU(emb) -> all 22 time_emb_proj at once
+        emb = self.buf("temb.sin", self.nb, c0)
+        ops.timestep_embed(self.t_table, self.step_idx, emb)
+        e1 = self.buf("temb.e1", self.nb, cfg.time_embed_dim)
+        ops.gemm(emb, W["time_embedding.linear_1.w"], e1, bias=W["time_embedding.linear_1.b"], silu=True)
+        e2 = self.buf("temb.e2", self.nb, cfg.time_embed_dim)
+        ops.gemm(e1, W["time_embedding.linear_2.w"], e2, bias=W["time_embedding.linear_2.b"], silu=True)
+        self.temb_all = self.buf("temb.all", self.nb, W.temb_total)
+        ops.gemm(e2, W["temb_all.w"], self.temb_all, bias=W["temb_all.b"])
+        # conv_in + mask_cond_fea (unet_3d.py:603-605)
+        cols = self.buf("im2col", B * L0, 64)
+        ops.im2col_latent(self.latents, cols, batch=self.nb)
+        x = self.buf("x.conv_in", B * L0, c0)
+        ops.gemm(cols, W["conv_in.w"], x, bias=W["conv_in.b"], residual=self.window["mask_cond"])
+        skips: List[Tuple[torch.Tensor, int]] = [(x, c0)]
+        level = 0
+        for b in W.blocks:
+            if b.kind in ("down_x", "down"):
+                for j, l in enumerate(b.layers):
+                    tag = f"skip.{b.name}.{j}"
+                    if b.kind == "down_x":
+                        x = self._cross_layer(b, l, x, None, level, tag)
+                    else:
+                        x = self._resnet(l.resnet, x, None, level, tag)         # Q1b: motion module skipped
+                    skips.append((x, b.channels))
+                if b.downsampler:
+                    hh, ww = self.level_hw[level]
+                    C = b.channels
+                    planes = self.buf("ds.planes", B * hh * ww, C)
+                    ops.phase_split(x.view(B, hh, ww, C), planes.view(4 * B, hh // 2, ww // 2, C))
+                    level += 1
+                    x = self.buf(f"skip.{b.name}.ds", B * self.L(level), C)
+                    ops.conv3x3_stride2(planes.view(4 * B, hh // 2, ww // 2, C), W[f"{b.downsampler}.conv.w"], x,
+                                        n=B, ho=hh // 2, wo=ww // 2, bias=W[f"{b.downsampler}.conv.b"])
+                    skips.append((x, C))
+            elif b.kind == "mid":
+                x = self._resnet(b.extra_resnet, x, None, level, "mid.rs0")
+                l = b.layers[0]
+                C = b.channels
+                x = self._spatial(l.attn, x, level, C, "lyr.sp")
+                x = self._audio(l.audio, x, level, C, l.audio_inner, b.depth, "lyr.au")
+                x = self._motion(l.motion, l.attn, x, level, C, "mid.mm")
+                x = self._resnet(l.resnet, x, None, level, "mid.out")
+            else:
+                for j, l in enumerate(b.layers):
+                    sk, _ = skips.pop()
+                    tag = f"up.{b.name}.{j % 2}"
+                    if b.kind == "up_x":
+                        x = self._cross_layer(b, l, x, sk, level, tag)
+                    else:
+                        x = self._resnet(l.resnet, x, sk, level, tag)           # Q1b
+                if b.upsampler:
+                    hh, ww = self.level_hw[level]
+                    C = b.channels
+                    up = self.buf("us.up", B * 4 * hh * ww, C)
+                    ops.upsample2x(x.view(B, hh, ww, C), up.view(B, 2 * hh, 2 * ww, C))
+                    level -= 1
+                    x = self.buf(f"up.{b.name}.us", B * self.L(level), C)
+                    ops.conv3x3(up.view(B, 2 * hh, 2 * ww, C), W[f"{b.upsampler}.conv.w"], x,
+                                bias=W[f"{b.upsampler}.conv.b"])
+        t = self.buf("out.gn", B * L0, c0)
+        self._gn(x, "conv_norm_out", t, B, L0, cfg.norm_eps, True)
+        self.model_out = self.buf("out.conv", B * L0, 8)
+        ops.conv3x3(t.view(B, h, w, c0), W["conv_out.w"], self.model_out, bias=W["conv_out.b"])
+        return self.model_out
+
+    @torch.no_grad()
+    def _step_tail(self):
+        """CFG combine + DDIM update + step counter (face_animate.py:415-420)."""
+        sh = self.shard
+        mo = self.model_out
+        if self.nb == 1:
+            # the two CFG halves live on different ranks: exchange the (tiny) model outputs
+            import torch.distributed as dist
+            allm = self.buf("out.all", sh.world_size * mo.shape[0], mo.shape[1])
+            dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1), group=sh.world)
+            gs = sh.group_size
+            me = sh.rank_in_group
+            n = mo.shape[0]
+            both = self.buf("out.both", 2 * n, mo.shape[1])
+            both[:n].copy_(allm[me * n:(me + 1) * n])                         # uncond group = ranks [0, gs)
+            both[n:].copy_(allm[(gs + me) * n:(gs + me + 1) * n])             # cond group = ranks [gs, 2gs)
+            mo = both
+        ops.cfg_ddim_step(mo, self.latents, self.coef, self.step_idx, guidance=self.guidance)
+        ops.advance_step(self.step_idx, self.n_steps)
+
+    # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def forward_only(self, latents: torch.Tensor, step: int = 0) -> torch.Tensor:
+        """UNet forward for the given fp32 latents [1, Cl, fl, h, w]; returns fp32 [nb, Cl, fl, h, w]."""
+        self.latents.copy_(latents.to(self.dev, torch.float32))
+        self.step_idx.fill_(step)
+        mo = self._forward()
+        out = torch.empty(self.nb, self.cfg.out_channels, self.fl, self.h, self.w, device=self.dev, dtype=torch.float32)
+        ops.tokens_to_bcfhw(mo, out)
+        return out
+
+    @torch.no_grad()
+    def capture(self):
+        """Warm up (allocates every buffer) and capture forward + CFG/DDIM step into one CUDA graph."""
+        lat0 = self.latents.clone()
+        st0 = self.step_idx.clone()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._forward()
+            self._step_tail()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.latents.copy_(lat0)
+        self.step_idx.copy_(st0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._forward()
+            self._step_tail()
+        self.graph = g
+        self.latents.copy_(lat0)
+        self.step_idx.copy_(st0)
+
+    @torch.no_grad()
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._forward()
+            self._step_tail()

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhallo_b200.so")
 
 HB_F16, HB_BF16 = 0, 1
 HB_EPI_GEGLU = 1
+HB_EPI_SILU = 2
 
 
 class GemmParams(C.Structure):
@@ -32,6 +33,21 @@ class GemmParams(C.Structure):
         ("flags", C.c_int32),
         ("conv3x3", C.c_int32),
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+    ]
+
+
+class AttentionParams(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("head_dim", C.c_int32), ("heads", C.c_int32),
+        ("L", C.c_int32), ("frames", C.c_int32),
+        ("Q", C.c_void_p), ("ldq", C.c_int64),
+        ("K", C.c_void_p), ("ldk", C.c_int64),
+        ("V", C.c_void_p), ("ldv", C.c_int64),
+        ("Kref", C.c_void_p), ("ldkref", C.c_int64),
+        ("Vref", C.c_void_p), ("ldvref", C.c_int64),
+        ("ref_frames", C.c_int32),
+        ("ref_index", C.c_void_p),
+        ("O", C.c_void_p), ("ldo", C.c_int64),
     ]
 
 

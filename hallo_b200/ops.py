@@ -10,7 +10,7 @@ from typing import Optional
 
 import torch
 
-from . import lib as L
+from . import lib
 
 
 def _rowmajor_ld(t: torch.Tensor) -> int:
@@ -21,31 +21,31 @@ def _rowmajor_ld(t: torch.Tensor) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          group_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0, alpha: float = 1.0,
-         geglu: bool = False, a2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         geglu: bool = False, silu: bool = False, a2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M, N(/2)] = epilogue(cat([a, a2], 1) @ w.T); see include/hallo_b200.h."""
-    p = L.GemmParams()
-    p.dtype = L.dtype_code(a.dtype)
+    p = lib.GemmParams()
+    p.dtype = lib.dtype_code(a.dtype)
     M, K1 = a.shape
     N, K = w.shape
     p.M, p.N, p.K = M, N, K
-    p.A, p.lda = L.ptr(a), _rowmajor_ld(a)
+    p.A, p.lda = lib.ptr(a), _rowmajor_ld(a)
     if a2 is not None:
         assert a2.shape[0] == M and K1 + a2.shape[1] == K
-        p.A2, p.lda2, p.K1 = L.ptr(a2), _rowmajor_ld(a2), K1
+        p.A2, p.lda2, p.K1 = lib.ptr(a2), _rowmajor_ld(a2), K1
     else:
         assert K1 == K, (K1, K)
-    p.W, p.ldw = L.ptr(w), _rowmajor_ld(w)
-    p.C, p.ldc = L.ptr(out), _rowmajor_ld(out)
+    p.W, p.ldw = lib.ptr(w), _rowmajor_ld(w)
+    p.C, p.ldc = lib.ptr(out), _rowmajor_ld(out)
     assert out.shape[0] == M and out.shape[1] == (N // 2 if geglu else N), (out.shape, M, N)
-    p.bias = L.ptr(bias)
+    p.bias = lib.ptr(bias)
     if group_bias is not None:
-        p.group_bias, p.ld_group_bias, p.rows_per_group = L.ptr(group_bias), _rowmajor_ld(group_bias), rows_per_group
-    p.row_scale = L.ptr(row_scale)
+        p.group_bias, p.ld_group_bias, p.rows_per_group = lib.ptr(group_bias), _rowmajor_ld(group_bias), rows_per_group
+    p.row_scale = lib.ptr(row_scale)
     if residual is not None:
-        p.residual, p.ldr = L.ptr(residual), _rowmajor_ld(residual)
+        p.residual, p.ldr = lib.ptr(residual), _rowmajor_ld(residual)
     p.alpha = alpha
-    p.flags = L.HB_EPI_GEGLU if geglu else 0
-    L.check(L.load().hallo_b200_gemm(C.byref(p), L.current_stream()), "gemm")
+    p.flags = (lib.HB_EPI_GEGLU if geglu else 0) | (lib.HB_EPI_SILU if silu else 0)
+    lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "gemm")
     return out
 
 
@@ -55,22 +55,22 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor, *, bias:
     """x: NHWC [n, h, w, cin]; w_packed: [cout, 9*cin] ([cout][kh][kw][cin]); out: [n*h*w, cout]."""
     n, h, w_, cin = x.shape
     assert x.stride(3) == 1 and x.stride(1) == w_ * x.stride(2) and x.stride(0) == h * x.stride(1)
-    p = L.GemmParams()
-    p.dtype = L.dtype_code(x.dtype)
+    p = lib.GemmParams()
+    p.dtype = lib.dtype_code(x.dtype)
     p.M, p.N, p.K = n * h * w_, w_packed.shape[0], w_packed.shape[1]
     assert p.K == 9 * cin
-    p.A, p.lda = L.ptr(x), x.stride(2)
-    p.W, p.ldw = L.ptr(w_packed), _rowmajor_ld(w_packed)
-    p.C, p.ldc = L.ptr(out), _rowmajor_ld(out)
-    p.bias = L.ptr(bias)
+    p.A, p.lda = lib.ptr(x), x.stride(2)
+    p.W, p.ldw = lib.ptr(w_packed), _rowmajor_ld(w_packed)
+    p.C, p.ldc = lib.ptr(out), _rowmajor_ld(out)
+    p.bias = lib.ptr(bias)
     if group_bias is not None:
-        p.group_bias, p.ld_group_bias, p.rows_per_group = L.ptr(group_bias), _rowmajor_ld(group_bias), rows_per_group
+        p.group_bias, p.ld_group_bias, p.rows_per_group = lib.ptr(group_bias), _rowmajor_ld(group_bias), rows_per_group
     if residual is not None:
-        p.residual, p.ldr = L.ptr(residual), _rowmajor_ld(residual)
+        p.residual, p.ldr = lib.ptr(residual), _rowmajor_ld(residual)
     p.alpha = 1.0
     p.conv3x3 = 1
     p.img_n, p.img_h, p.img_w = n, h, w_
-    L.check(L.load().hallo_b200_gemm(C.byref(p), L.current_stream()), "conv3x3")
+    lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "conv3x3")
     return out
 
 
@@ -88,3 +88,171 @@ def pack_geglu_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
     wi = torch.stack([w[:half], w[half:]], dim=1).reshape(n2, k).contiguous()
     bi = None if b is None else torch.stack([b[:half], b[half:]], dim=1).reshape(n2).contiguous()
     return wi, bi
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, L: int,
+              kref: Optional[torch.Tensor] = None, vref: Optional[torch.Tensor] = None,
+              ref_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v/out: [frames*L, C] row-major views (column slices of a fused buffer are fine).
+    kref/vref: [ref_frames*L, C]; ref_index: int32 [frames] device tensor (-1 = no reference keys)."""
+    p = lib.AttentionParams()
+    p.dtype = lib.dtype_code(q.dtype)
+    rows, Cq = q.shape
+    assert rows % L == 0 and Cq % heads == 0
+    p.head_dim, p.heads, p.L, p.frames = Cq // heads, heads, L, rows // L
+    p.Q, p.ldq = lib.ptr(q), _rowmajor_ld(q)
+    p.K, p.ldk = lib.ptr(k), _rowmajor_ld(k)
+    p.V, p.ldv = lib.ptr(v), _rowmajor_ld(v)
+    p.O, p.ldo = lib.ptr(out), _rowmajor_ld(out)
+    if ref_index is not None:
+        assert ref_index.dtype == torch.int32 and ref_index.numel() == p.frames and ref_index.is_cuda
+        p.Kref, p.ldkref = lib.ptr(kref), _rowmajor_ld(kref)
+        p.Vref, p.ldvref = lib.ptr(vref), _rowmajor_ld(vref)
+        p.ref_frames = kref.shape[0] // L
+        p.ref_index = lib.ptr(ref_index)
+    lib.check(lib.load().hallo_b200_attention(C.byref(p), lib.current_stream()), "attention")
+    return out
+
+
+# ----------------------------------------------------------------------------- aux kernels (csrc/aux.cu)
+def _i(v) -> C.c_int:
+    return C.c_int(int(v))
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, eps: float = 1e-5,
+              pe: Optional[torch.Tensor] = None, pe_index: Optional[torch.Tensor] = None, tokens_per_frame: int = 0,
+              frames: int = 0) -> torch.Tensor:
+    rows, Cc = x.shape
+    if pe is not None:
+        assert pe.dtype == torch.float32 and pe.is_contiguous() and pe.shape[-1] == Cc
+    lib.check(lib.load().hallo_b200_layernorm(
+        _i(lib.dtype_code(x.dtype)), C.c_void_p(lib.ptr(x)), C.c_int64(_rowmajor_ld(x)), C.c_void_p(lib.ptr(out)),
+        C.c_int64(_rowmajor_ld(out)), C.c_void_p(lib.ptr(gamma)), C.c_void_p(lib.ptr(beta)), _i(rows), _i(Cc),
+        C.c_float(eps), C.c_void_p(lib.ptr(pe)), C.c_void_p(lib.ptr(pe_index)), _i(tokens_per_frame), _i(frames),
+        lib.current_stream()), "layernorm")
+    return out
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, stats_ws: torch.Tensor, *,
+              n_frames: int, hw: int, groups: int = 32, eps: float = 1e-5, silu: bool = False,
+              x2: Optional[torch.Tensor] = None, fpb_in: int = 0, fpb_out: int = 0, frame_off: int = 0) -> torch.Tensor:
+    """x1: [n_frames*hw, C1] contiguous, x2: optional [n_frames*hw, C2]; out: [*, C1+C2] contiguous."""
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous()) and out.is_contiguous()
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= 2 * n_frames * groups
+    C1 = x1.shape[1]
+    C2 = 0 if x2 is None else x2.shape[1]
+    lib.check(lib.load().hallo_b200_groupnorm(
+        _i(lib.dtype_code(x1.dtype)), C.c_void_p(lib.ptr(x1)), _i(C1), C.c_void_p(lib.ptr(x2)), _i(C2), _i(n_frames),
+        _i(hw), _i(groups), C.c_void_p(lib.ptr(gamma)), C.c_void_p(lib.ptr(beta)), C.c_float(eps), _i(1 if silu else 0),
+        C.c_void_p(lib.ptr(out)), C.c_void_p(lib.ptr(stats_ws)), _i(fpb_in), _i(fpb_out), _i(frame_off),
+        lib.current_stream()), "groupnorm")
+    return out
+
+
+def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, frames: int, tokens: int,
+                    heads: int, head_dim: int, n_keys: int, kv_frame_div: int = 1, regions: int = 1,
+                    q_region_stride: int = 0, kv_region_stride: int = 0, o_region_stride: int = 0) -> torch.Tensor:
+    """q/out: [frames*tokens, ld]; k/v: [kv_frames*n_keys, ldkv] (same ld for both)."""
+    assert _rowmajor_ld(k) == _rowmajor_ld(v)
+    lib.check(lib.load().hallo_b200_cross_attention(
+        _i(lib.dtype_code(q.dtype)), C.c_void_p(lib.ptr(q)), C.c_int64(_rowmajor_ld(q)), _i(q_region_stride),
+        C.c_void_p(lib.ptr(k)), C.c_void_p(lib.ptr(v)), C.c_int64(_rowmajor_ld(k)), _i(kv_region_stride),
+        C.c_void_p(lib.ptr(out)), C.c_int64(_rowmajor_ld(out)), _i(o_region_stride), _i(frames), _i(tokens), _i(heads),
+        _i(head_dim), _i(n_keys), _i(kv_frame_div), _i(regions), lib.current_stream()), "cross_attention")
+    return out
+
+
+def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, batch: int, fq: int,
+                       fk: int, tokens: int, heads: int) -> torch.Tensor:
+    """q/out: [batch*fq*tokens, ld]; k/v: [batch*fk*tokens, ldkv]."""
+    assert _rowmajor_ld(k) == _rowmajor_ld(v)
+    head_dim = out.shape[1] // heads
+    lib.check(lib.load().hallo_b200_temporal_attention(
+        _i(lib.dtype_code(q.dtype)), C.c_void_p(lib.ptr(q)), C.c_int64(_rowmajor_ld(q)), C.c_void_p(lib.ptr(k)),
+        C.c_void_p(lib.ptr(v)), C.c_int64(_rowmajor_ld(k)), C.c_void_p(lib.ptr(out)), C.c_int64(_rowmajor_ld(out)),
+        _i(batch), _i(fq), _i(fk), _i(tokens), _i(heads), _i(head_dim), lib.current_stream()), "temporal_attention")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.numel() == 4 * x.numel()
+    lib.check(lib.load().hallo_b200_upsample2x(_i(lib.dtype_code(x.dtype)), C.c_void_p(lib.ptr(x)),
+                                               C.c_void_p(lib.ptr(out)), _i(n), _i(h), _i(w), _i(c),
+                                               lib.current_stream()), "upsample2x")
+    return out
+
+
+def phase_split(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
+    lib.check(lib.load().hallo_b200_phase_split(_i(lib.dtype_code(x.dtype)), C.c_void_p(lib.ptr(x)),
+                                                C.c_void_p(lib.ptr(out)), _i(n), _i(h), _i(w), _i(c),
+                                                lib.current_stream()), "phase_split")
+    return out
+
+
+def conv3x3_stride2(x_planes: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor, *, n: int, ho: int, wo: int,
+                    bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x_planes: phase planes [4*n, ho, wo, cin] from phase_split; out: [n*ho*wo, cout]."""
+    cin = x_planes.shape[-1]
+    assert x_planes.is_contiguous() and x_planes.shape[0] == 4 * n
+    p = lib.GemmParams()
+    p.dtype = lib.dtype_code(x_planes.dtype)
+    p.M, p.N, p.K = n * ho * wo, w_packed.shape[0], w_packed.shape[1]
+    assert p.K == 9 * cin
+    p.A, p.lda = lib.ptr(x_planes), cin
+    p.W, p.ldw = lib.ptr(w_packed), _rowmajor_ld(w_packed)
+    p.C, p.ldc = lib.ptr(out), _rowmajor_ld(out)
+    p.bias = lib.ptr(bias)
+    p.alpha = 1.0
+    p.conv3x3 = 2
+    p.img_n, p.img_h, p.img_w = n, ho, wo
+    lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "conv3x3_stride2")
+    return out
+
+
+def im2col_latent(latents: torch.Tensor, out: torch.Tensor, *, batch: int) -> torch.Tensor:
+    """latents: fp32 [1, Cl, F, H, W] contiguous; out: [batch*F*H*W, 64]."""
+    _, cl, f, h, w = latents.shape
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and out.is_contiguous()
+    lib.check(lib.load().hallo_b200_im2col_latent(_i(lib.dtype_code(out.dtype)), C.c_void_p(lib.ptr(latents)),
+                                                  C.c_void_p(lib.ptr(out)), _i(batch), _i(cl), _i(f), _i(h), _i(w),
+                                                  lib.current_stream()), "im2col_latent")
+    return out
+
+
+def timestep_embed(t_table: torch.Tensor, step: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    rows, dim = out.shape
+    assert t_table.dtype == torch.float32 and step.dtype == torch.int32 and out.is_contiguous()
+    lib.check(lib.load().hallo_b200_timestep_embed(_i(lib.dtype_code(out.dtype)), C.c_void_p(lib.ptr(t_table)),
+                                                   C.c_void_p(lib.ptr(step)), C.c_void_p(lib.ptr(out)), _i(rows),
+                                                   _i(dim), lib.current_stream()), "timestep_embed")
+    return out
+
+
+def cfg_ddim_step(model_out: torch.Tensor, latents: torch.Tensor, coef: torch.Tensor, step: torch.Tensor, *,
+                  guidance: float, v_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """model_out: [2*F*HW, ld] tokens (uncond rows then cond rows); latents: fp32 [1, Cl, F, H, W] updated in place."""
+    _, cl, f, h, w = latents.shape
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and coef.dtype == torch.float32
+    lib.check(lib.load().hallo_b200_cfg_ddim_step(
+        _i(lib.dtype_code(model_out.dtype)), C.c_void_p(lib.ptr(model_out)), C.c_int64(_rowmajor_ld(model_out)),
+        C.c_void_p(lib.ptr(latents)), C.c_void_p(lib.ptr(coef)), C.c_void_p(lib.ptr(step)), C.c_float(guidance), _i(cl),
+        _i(f), _i(h * w), C.c_void_p(lib.ptr(v_out)), lib.current_stream()), "cfg_ddim_step")
+    return latents
+
+
+def advance_step(step: torch.Tensor, n_steps: int) -> None:
+    lib.check(lib.load().hallo_b200_advance_step(C.c_void_p(lib.ptr(step)), _i(n_steps), lib.current_stream()),
+              "advance_step")
+
+
+def tokens_to_bcfhw(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x: [B*F*HW, ld] tokens (first C columns used); out: fp32 [B, C, F, H, W]."""
+    b, c, f, h, w = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    lib.check(lib.load().hallo_b200_tokens_to_bcfhw(_i(lib.dtype_code(x.dtype)), C.c_void_p(lib.ptr(x)),
+                                                    C.c_int64(_rowmajor_ld(x)), C.c_void_p(lib.ptr(out)), _i(b), _i(c),
+                                                    _i(f), _i(h * w), lib.current_stream()), "tokens_to_bcfhw")
+    return out

@@ -63,8 +63,11 @@ int64_t hallo_b200_launch_count(int reset);
  *        A2 for k >= K1) -- the UNet skip-connection channel concat without a copy
  *        (hallo/models/unet_3d_blocks.py:1131,1373).
  *   W  : [N, K] row-major (torch Linear layout; conv weights packed [Cout][tap][Cin]).
- *   conv3x3 != 0: A is an NHWC image batch [img_n, img_h, img_w, Cin]; M = img_n*img_h*img_w,
+ *   conv3x3 == 1: A is an NHWC image batch [img_n, img_h, img_w, Cin]; M = img_n*img_h*img_w,
  *        K = 9*Cin; stride 1, zero padding 1 (TMA out-of-bounds fill).
+ *   conv3x3 == 2: stride-2 conv (Downsample3D, resnet.py:232-252).  A holds the 4 phase planes
+ *        written by hallo_b200_phase_split: [4*img_n, img_h, img_w, Cin] where img_h/img_w are
+ *        the OUTPUT height/width; M = img_n*img_h*img_w.
  *   epilogue, in this order (each optional):
  *        v  = acc + bias[col] + group_bias[row / rows_per_group][col]
  *        v  = v_even * gelu_erf(v_odd)           (HB_EPI_GEGLU: W rows interleaved value/gate,
@@ -72,7 +75,7 @@ int64_t hallo_b200_launch_count(int reset);
  *        v  = v * row_scale[row] * alpha + residual[row][col]
  *   Constraints: K % 64 == 0 (K1 % 64 == 0, Cin % 64 == 0); lda/ldw/ldc/ldr % 8 == 0.
  * ---------------------------------------------------------------------------------------- */
-enum hb_epi_flags { HB_EPI_GEGLU = 1 };
+enum hb_epi_flags { HB_EPI_GEGLU = 1, HB_EPI_SILU = 2 /* v = silu(v) right after the bias adds */ };
 
 typedef struct {
   int32_t dtype;
@@ -100,6 +103,100 @@ typedef struct {
 } hb_gemm_params;
 
 int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * hallo_b200_attention -- fused softmax(Q K^T / sqrt(d)) V, tcgen05 + TMEM, flash-style.
+ *
+ * Replaces diffusers Attention/AttnProcessor2_0 SDPA at
+ *   hallo/models/mutual_self_attention.py:253-286  spatial self-attention with ReferenceNet KV concat
+ *                                                  (and the uncond-half recomputation, Q3)
+ *   hallo/models/attention.py:828-831              audio-block self-attention
+ *
+ *   Q, K, V : token matrices [frames*L, ld*], head h occupies columns [h*head_dim, (h+1)*head_dim)
+ *             (they may be column slices of one fused QKV projection buffer).
+ *   Kref/Vref: [ref_frames*L, ld*ref] reference tokens, projected once per window.
+ *   ref_index: int32 [frames] on the device; frame n attends to its own L keys and, when
+ *             ref_index[n] >= 0, additionally to the L keys of reference frame ref_index[n]
+ *             (the reference tiles CFG halves over the batch: ref_index[n] = n % 2 for cond
+ *             frames, -1 for uncond frames -- SURVEY quirk Q9).  NULL = plain self-attention.
+ *   O       : [frames*L, ldo], same head layout.
+ *   head_dim in {40, 80, 160}; scale = head_dim^-0.5; no mask, no dropout.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;
+  int32_t head_dim, heads;
+  int32_t L, frames;
+  const void* Q;
+  int64_t ldq;
+  const void* K;
+  int64_t ldk;
+  const void* V;
+  int64_t ldv;
+  const void* Kref;
+  int64_t ldkref;
+  const void* Vref;
+  int64_t ldvref;
+  int32_t ref_frames;
+  const int32_t* ref_index;
+  void* O;
+  int64_t ldo;
+} hb_attention_params;
+
+int hallo_b200_attention(const hb_attention_params* p, hb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound helpers (csrc/aux.cu)
+ * ---------------------------------------------------------------------------------------- */
+/* nn.LayerNorm(C, eps) per token row; optional `+ pe[pe_index[(row / L) % frames]]` after the norm
+ * (PositionalEncoding of hallo/models/motion_module.py:426-461, applied at :585-586).
+ * pe: fp32 [max_len, C] or NULL; pe_index: int32 [frames] or NULL (identity). */
+int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void* out, int64_t ldo, const void* gamma,
+                         const void* beta, int rows, int C, float eps, const float* pe,
+                         const int32_t* pe_index, int L, int frames, hb_stream_t stream);
+
+/* Per-frame GroupNorm over channels-last frames [N, HW, C1(+C2)] (InflatedGroupNorm, resnet.py:88-101;
+ * transformer_3d.py:197; motion_module.py:290), optional SiLU (resnet.py:386-387, 399).
+ * x2/C2: second channel-concatenated source (UNet skip connection) or NULL/0.
+ * stats_ws: fp32 [N*G*2] workspace.  Output frame n -> (n / fpb_in) * fpb_out + frame_off + n % fpb_in
+ * (fpb_in <= 0: identity) -- used to drop frames into the 18-frame temporal buffer. */
+int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, int N, int HW, int G,
+                         const void* gamma, const void* beta, float eps, int silu, void* out,
+                         float* stats_ws, int fpb_in, int fpb_out, int frame_off, hb_stream_t stream);
+
+/* softmax(q k^T / sqrt d) v against n_keys in {4, 32} keys per (kv-frame, head, region):
+ * image-token cross-attention (mutual_self_attention.py:289-303) and the three audio cross-attentions
+ * (attention.py:854-890).  Frame n reads keys of kv-frame n / kv_frame_div.  Region r reads Q columns
+ * at r*q_region_stride, K/V columns at r*kv_region_stride, writes O columns at r*o_region_stride. */
+int hallo_b200_cross_attention(int dtype, const void* Q, int64_t ldq, int q_region_stride, const void* K,
+                               const void* V, int64_t ldkv, int kv_region_stride, void* O, int64_t ldo,
+                               int o_region_stride, int frames, int L, int heads, int head_dim, int n_keys,
+                               int kv_frame_div, int regions, hb_stream_t stream);
+
+/* Temporal self-attention over the frame axis at every pixel (VersatileAttention,
+ * motion_module.py:579-609).  Q: [batch*Fq*L, ldq]; K/V: [batch*Fk*L, ldkv]; Fk <= 32. */
+int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t ldq, const void* K, const void* V,
+                                  int64_t ldkv, void* O, int64_t ldo, int batch, int Fq, int Fk, int L,
+                                  int heads, int head_dim, hb_stream_t stream);
+
+/* F.interpolate(scale 2, nearest) on NHWC (Upsample3D, resnet.py:166-183). */
+int hallo_b200_upsample2x(int dtype, const void* x, void* out, int N, int H, int W, int C, hb_stream_t stream);
+/* space-to-depth phase planes feeding the stride-2 conv (conv3x3 == 2). */
+int hallo_b200_phase_split(int dtype, const void* x, void* out, int N, int H, int W, int C, hb_stream_t stream);
+/* im2col of the fp32 latents [1, Cl, F, H, W] for conv_in (unet_3d.py:603): out [batch*F*H*W, 64]. */
+int hallo_b200_im2col_latent(int dtype, const float* latents, void* out, int batch, int Cl, int F, int H,
+                             int W, hb_stream_t stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, shift 0) for t = t_table[*step] (unet_3d.py:565-587). */
+int hallo_b200_timestep_embed(int dtype, const float* t_table, const int32_t* step, void* out, int rows,
+                              int dim, hb_stream_t stream);
+/* CFG combine + DDIM v-prediction update on fp32 latents [1, Cl, F, HW] (face_animate.py:415-420).
+ * coef: fp32 [n_steps, 4] = sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev). */
+int hallo_b200_cfg_ddim_step(int dtype, const void* model_out, int64_t ldm, float* latents, const float* coef,
+                             const int32_t* step, float guidance, int Cl, int F, int HW, float* v_out,
+                             hb_stream_t stream);
+int hallo_b200_advance_step(int32_t* step, int n_steps, hb_stream_t stream);
+/* channels-last [B*F*HW, ld] (first C columns) -> fp32 [B, C, F, HW] (the reference's output layout). */
+int hallo_b200_tokens_to_bcfhw(int dtype, const void* x, int64_t ld, float* out, int B, int C, int F, int HW,
+                               hb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,33 @@ def bench_conv():
         report(f"conv3x3 n{n} {h}x{h} {cin}->{cout}", ms, 2.0 * n * h * h * 9 * cin * cout)
 
 
+
+
+def bench_attn():
+    dev = "cuda"
+    for (C, L, frames, with_ref) in [(320, 4096, 32, True), (320, 4096, 32, False), (640, 1024, 32, True),
+                                     (1280, 256, 32, True), (1280, 64, 32, True)]:
+        qkv = torch.randn(frames * L, 3 * C, device=dev, dtype=torch.float16)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        kvref = torch.randn(2 * L, 2 * C, device=dev, dtype=torch.float16)
+        out = torch.empty(frames * L, C, device=dev, dtype=torch.float16)
+        ridx = torch.tensor([-1] * (frames // 2) + [n % 2 for n in range(frames // 2)], dtype=torch.int32, device=dev)
+        if with_ref:
+            fn = lambda: ops.attention(q, k, v, out, heads=8, L=L, kref=kvref[:, :C], vref=kvref[:, C:], ref_index=ridx)
+            flops = 4.0 * (frames // 2) * L * (2 * L) * C + 4.0 * (frames // 2) * L * L * C
+        else:
+            fn = lambda: ops.attention(q, k, v, out, heads=8, L=L)
+            flops = 4.0 * frames * L * L * C
+        ms = timeit(fn)
+        report(f"attn C{C} L{L} f{frames} ref={with_ref}", ms, flops)
+        if not with_ref:
+            qh = q.reshape(frames, L, 8, C // 8).transpose(1, 2)
+            kh = k.reshape(frames, L, 8, C // 8).transpose(1, 2)
+            vh = v.reshape(frames, L, 8, C // 8).transpose(1, 2)
+            ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
+            report("  torch sdpa same shape", ms, flops)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "conv"]
     for wname in which:
