@@ -392,7 +392,7 @@ __global__ void phase_split_kernel(const T* __restrict__ x, T* __restrict__ out,
 // latents: fp32 [1, Cl, F, H, W]; both CFG halves see the same latents (face_animate.py:398).
 template <typename T>
 __global__ void im2col_latent_kernel(const float* __restrict__ lat, T* __restrict__ out, int batch,
-                                     int Cl, int F, int H, int W) {
+                                     int Cl, int F, int H, int W, long long batch_stride) {
   const long long total = (long long)batch * F * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -401,6 +401,7 @@ __global__ void im2col_latent_kernel(const float* __restrict__ lat, T* __restric
   const int h = (int)(t % H);
   t /= H;
   const int f = (int)(t % F);
+  lat += (t / F) * batch_stride;
   float v[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) v[j] = 0.f;
@@ -656,13 +657,14 @@ extern "C" int hallo_b200_phase_split(int dtype, const void* x, void* out, int N
 }
 
 extern "C" int hallo_b200_im2col_latent(int dtype, const float* latents, void* out, int batch, int Cl,
-                                        int F, int H, int W, hb_stream_t stream) {
+                                        int F, int H, int W, int per_half_latents, hb_stream_t stream) {
   if (!latents || !out) return fail(HB_ERR_NULL, "im2col_latent: null pointer");
   if (Cl * 9 > 64) return fail(HB_ERR_BAD_SHAPE, "im2col_latent: Cl=%d", Cl);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)batch * F * H * W;
   HB_DISPATCH_T(dtype, {
-    im2col_latent_kernel<T><<<(int)((total + 127) / 128), 128, 0, s>>>(latents, (T*)out, batch, Cl, F, H, W);
+    im2col_latent_kernel<T><<<(int)((total + 127) / 128), 128, 0, s>>>(
+        latents, (T*)out, batch, Cl, F, H, W, per_half_latents ? (long long)Cl * F * H * W : 0LL);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;

@@ -195,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (it >> 1) & 1;
       const int r_in_tile = quarter * 32 + lane;
       long long row;
+      bool row_ok;
       if (CONV) {
         int per_img = p.tiles_w * p.tiles_h;
         int nb = tm / per_img;
@@ -205,12 +206,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int r2 = r_in_tile - dn * (p.box_h * p.box_w);
         int dh = r2 / p.box_w;
         int dw = r2 - dh * p.box_w;
-        row = ((long long)(nb * p.box_n + dn) * p.img_h + (hb_ * p.box_h + dh)) * p.img_w +
-              (wb * p.box_w + dw);
+        const int in_ = nb * p.box_n + dn, ih = hb_ * p.box_h + dh, iw = wb * p.box_w + dw;
+        row = ((long long)in_ * p.img_h + ih) * p.img_w + iw;
+        row_ok = in_ < p.img_n && ih < p.img_h && iw < p.img_w;   // boxes may overhang the image batch
       } else {
         row = (long long)tm * kBM + r_in_tile;
+        row_ok = row < p.M;
       }
-      const bool row_ok = row < p.M;
       float rs = p.alpha;
       if (rscale != nullptr && row_ok) rs *= Cvt<T>::to_f(rscale[row]);
       const T* gb_row = nullptr;
@@ -322,22 +324,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// pick an NHWC box (box_w, box_h, box_n) of 128 pixels that tiles the image batch exactly
-static bool pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
-  for (int cw = 128; cw >= 1; cw >>= 1) {
-    if (w % cw != 0) continue;
-    int rest = 128 / cw;
-    for (int ch = rest; ch >= 1; ch >>= 1) {
-      if (h % ch != 0) continue;
-      int cn = rest / ch;
-      if (n % cn != 0) continue;
-      *bw = cw;
-      *bh = ch;
-      *bn = cn;
-      return true;
+// pick the NHWC box (box_w, box_h, box_n), box_w*box_h*box_n == 128, that covers the image batch with the
+// fewest tiles; boxes may overhang (TMA zero-fills, the epilogue masks), so any image size works.
+static void pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int cw = 1; cw <= 128; cw <<= 1)
+    for (int ch = 1; cw * ch <= 128; ch <<= 1) {
+      const int cn = 128 / (cw * ch);
+      const long long tiles = (long long)((w + cw - 1) / cw) * ((h + ch - 1) / ch) * ((n + cn - 1) / cn);
+      // prefer wider boxes on ties (longer contiguous TMA rows)
+      if (best < 0 || tiles < best || (tiles == best && cw > *bw)) {
+        best = tiles;
+        *bw = cw;
+        *bh = ch;
+        *bn = cn;
+      }
     }
-  }
-  return false;
 }
 
 template <typename T, int BN, int STAGES>
@@ -375,10 +377,8 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
       return fail(HB_ERR_BAD_SHAPE, "conv3x3 needs Cin %% 64 == 0 (K=%d)", q->K);
     if ((long long)q->img_n * q->img_h * q->img_w != q->M)
       return fail(HB_ERR_BAD_SHAPE, "conv3x3 M=%d != n*h*w", q->M);
-    int bw, bh, bn;
-    if (!pick_conv_box(q->img_n, q->img_h, q->img_w, &bw, &bh, &bn))
-      return fail(HB_ERR_BAD_SHAPE, "conv3x3: no 128-pixel box tiles %dx%dx%d", q->img_n, q->img_h,
-                  q->img_w);
+    int bw = 1, bh = 1, bn = 128;
+    pick_conv_box(q->img_n, q->img_h, q->img_w, &bw, &bh, &bn);
     d.cin = cin;
     d.img_n = q->img_n;
     d.stride2 = q->conv3x3 == 2 ? 1 : 0;
@@ -387,9 +387,9 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
     d.box_w = bw;
     d.box_h = bh;
     d.box_n = bn;
-    d.tiles_w = q->img_w / bw;
-    d.tiles_h = q->img_h / bh;
-    d.tiles_m = d.tiles_w * d.tiles_h * (q->img_n / bn);
+    d.tiles_w = (q->img_w + bw - 1) / bw;
+    d.tiles_h = (q->img_h + bh - 1) / bh;
+    d.tiles_m = d.tiles_w * d.tiles_h * ((q->img_n + bn - 1) / bn);
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)q->img_w, (uint64_t)q->img_h,
                         (uint64_t)q->img_n * (q->conv3x3 == 2 ? 4 : 1)};
     uint64_t str[3] = {(uint64_t)q->lda * 2, (uint64_t)q->lda * 2 * q->img_w,

@@ -209,6 +209,7 @@ class DenoiseEngine:
         self.guidance = 1.0
         self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
         self.model_out: Optional[torch.Tensor] = None
+        self.sample: Optional[torch.Tensor] = None      # per-half fp32 sample for the plain forward() API path
 
     # ------------------------------------------------------------------ buffers
     def buf(self, tag: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
@@ -218,6 +219,17 @@ class DenoiseEngine:
             t = torch.empty(rows, cols, device=self.dev, dtype=dtype or self.dtype)
             self._bufs[key] = t
         return t
+
+    def _wset(self, key: str, t: torch.Tensor) -> torch.Tensor:
+        """Window constants live in persistent buffers (updated in place) so a captured graph stays valid."""
+        cur = self.window.get(key)
+        if isinstance(cur, torch.Tensor) and cur.shape == t.shape and cur.dtype == t.dtype:
+            cur.copy_(t)
+            return cur
+        self.window[key] = t.clone() if t._base is not None or not t.is_contiguous() else t
+        if isinstance(cur, torch.Tensor):
+            self.graph = None            # shapes changed: any captured graph is stale
+        return self.window[key]
 
     def L(self, level: int) -> int:
         hh, ww = self.level_hw[level]
@@ -247,9 +259,9 @@ class DenoiseEngine:
         win["row_ids"] = rows
         # reference tiles CFG halves over the batch (Q9): row n attends to ref[n % 2]; uncond rows: none (Q3)
         ridx = [(-1 if n < f else (n % 2)) for n in rows]
-        win["ref_index"] = torch.tensor(ridx, dtype=torch.int32, device=dev)
+        self._wset("ref_index", torch.tensor(ridx, dtype=torch.int32, device=dev))
         # temporal positions: motion frames 0..nm-1, then nm + global frame id
-        win["pe_index"] = torch.tensor(list(range(nm)) + [nm + g for g in frames], dtype=torch.int32, device=dev)
+        self._wset("pe_index", torch.tensor(list(range(nm)) + [nm + g for g in frames], dtype=torch.int32, device=dev))
 
         ehs = encoder_hidden_states.to(dev, dt)[halves]                       # [nb, 4, 768]
         aud = audio_embedding.to(dev, dt)[halves][:, fr_idx]                  # [nb, fl, 32, 768]
@@ -258,11 +270,11 @@ class DenoiseEngine:
         win["n_img_tokens"] = ehs.shape[1]
         win["n_aud_tokens"] = aud.shape[2]
         mcf = mask_cond_fea.to(dev, dt)[halves][:, :, fr_idx]                 # [nb, C0, fl, h, w]
-        win["mask_cond"] = mcf.permute(0, 2, 3, 4, 1).reshape(-1, mcf.shape[1]).contiguous()
+        self._wset("mask_cond", mcf.permute(0, 2, 3, 4, 1).reshape(-1, mcf.shape[1]).contiguous())
         rid = torch.tensor(rows, device=dev)
         for nme, m in (("full", full_mask), ("face", face_mask), ("lip", lip_mask)):
             for lv, t in enumerate(m):
-                win[f"mask.{nme}.{lv}"] = t.to(dev, dt)[rid].reshape(-1).contiguous()
+                self._wset(f"mask.{nme}.{lv}", t.to(dev, dt)[rid].reshape(-1).contiguous())
         ms = [float(x) for x in motion_scale] if motion_scale is not None else [1.0, 1.0, 1.0]
 
         for b in W.blocks:
@@ -275,23 +287,23 @@ class DenoiseEngine:
                     bank = banks[l.attn].to(dev, torch.float16).to(dt)          # update() casts to fp16 (Q4)
                     bank = bank.reshape(2, 1 + nm, L, C)
                     refs = bank[:, 0].reshape(2 * L, C).contiguous()           # both CFG halves' ref tokens
-                    kv = torch.empty(2 * L, 2 * C, device=dev, dtype=dt)
+                    kv = self.buf(f"{l.attn}.kvref", 2 * L, 2 * C)
                     ops.gemm(refs, W[f"{tb}.attn1.kv"], kv)
                     win[f"{l.attn}.kvref"] = kv
-                    kvi = torch.empty(ehs2.shape[0], 2 * C, device=dev, dtype=dt)
+                    kvi = self.buf(f"{l.attn}.kvimg", ehs2.shape[0], 2 * C)
                     ops.gemm(ehs2, W[f"{tb}.attn2.kv"], kvi)
                     win[f"{l.attn}.kvimg"] = kvi
                     # motion-frame features of the local halves, token layout [nb*nm*L, C]
-                    win[f"{l.attn}.motion"] = bank[halves][:, 1:].reshape(nb * nm * L, C).contiguous()
+                    self._wset(f"{l.attn}.motion", bank[halves][:, 1:].reshape(nb * nm * L, C).contiguous())
                 if l.audio:
                     tb = f"{l.audio}.transformer_blocks.0"
                     Ci = l.audio_inner
-                    kva = torch.empty(aud2.shape[0], 6 * Ci, device=dev, dtype=dt)
+                    kva = self.buf(f"{l.audio}.kvaud", aud2.shape[0], 6 * Ci)
                     ops.gemm(aud2, W[f"{tb}.attn2.kv6"], kva)
                     win[f"{l.audio}.kvaud"] = kva
                     zw, zb = W[f"{tb}.zero.w"], W[f"{tb}.zero.b"]
-                    win[f"{l.audio}.zero.w"] = torch.cat([ms[r] * zw[r] for r in range(3)], 1).to(dt).contiguous()
-                    win[f"{l.audio}.zero.b"] = sum(ms[r] * zb[r] for r in range(3)).to(dt).contiguous()
+                    self._wset(f"{l.audio}.zero.w", torch.cat([ms[r] * zw[r] for r in range(3)], 1).to(dt).contiguous())
+                    self._wset(f"{l.audio}.zero.b", sum(ms[r] * zb[r] for r in range(3)).to(dt).contiguous())
                 if l.motion and l.motion_executed:
                     # GroupNorm of the motion frames is step-invariant: normalise once into frames [0, nm)
                     tt = f"{l.motion}.temporal_transformer"
@@ -497,7 +509,7 @@ class DenoiseEngine:
         ops.gemm(e2, W["temb_all.w"], self.temb_all, bias=W["temb_all.b"])
         # conv_in + mask_cond_fea (unet_3d.py:603-605)
         cols = self.buf("im2col", B * L0, 64)
-        ops.im2col_latent(self.latents, cols, batch=self.nb)
+        ops.im2col_latent(self.sample if self.sample is not None else self.latents, cols, batch=self.nb)
         x = self.buf("x.conv_in", B * L0, c0)
         ops.gemm(cols, W["conv_in.w"], x, bias=W["conv_in.b"], residual=self.window["mask_cond"])
         skips: List[Tuple[torch.Tensor, int]] = [(x, c0)]
@@ -575,10 +587,18 @@ class DenoiseEngine:
     # ------------------------------------------------------------------ public
     @torch.no_grad()
     def forward_only(self, latents: torch.Tensor, step: int = 0) -> torch.Tensor:
-        """UNet forward for the given fp32 latents [1, Cl, fl, h, w]; returns fp32 [nb, Cl, fl, h, w]."""
-        self.latents.copy_(latents.to(self.dev, torch.float32))
+        """UNet forward for fp32 latents [1, Cl, fl, h, w] (shared by the CFG halves) or a full per-half sample
+        [nb, Cl, fl, h, w]; returns fp32 [nb, Cl, fl, h, w]."""
+        latents = latents.to(self.dev, torch.float32).contiguous()
+        if latents.shape[0] == 1:
+            self.latents.copy_(latents)
+            self.sample = None
+        else:
+            assert latents.shape[0] == self.nb
+            self.sample = latents
         self.step_idx.fill_(step)
         mo = self._forward()
+        self.sample = None
         out = torch.empty(self.nb, self.cfg.out_channels, self.fl, self.h, self.w, device=self.dev, dtype=torch.float32)
         ops.tokens_to_bcfhw(mo, out)
         return out

@@ -13,11 +13,34 @@ import torch
 from . import lib
 
 
+# Optional per-op timing (bench.py / tools): set PROFILE = [] to collect (name, start_event, end_event).
+PROFILE = None
+
+
+def _timed(name_fn):
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            if PROFILE is None:
+                return fn(*args, **kwargs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kwargs)
+            e1.record()
+            PROFILE.append((name_fn(*args, **kwargs), e0, e1))
+            return out
+        return wrapper
+    return deco
+
+
 def _rowmajor_ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and t.stride(1) == 1, f"need row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
     return t.stride(0)
 
 
+@_timed(lambda a, w, out, **kw: f"gemm M{a.shape[0]} N{w.shape[0]} K{w.shape[1]}" + (" geglu" if kw.get("geglu") else ""))
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          group_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0, alpha: float = 1.0,
@@ -49,17 +72,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     return out
 
 
+@_timed(lambda x, w, out, **kw: f"conv3x3 n{x.shape[0]} {x.shape[1]}x{x.shape[2]} {x.shape[3]}->{w.shape[0]}")
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
             residual: Optional[torch.Tensor] = None, group_bias: Optional[torch.Tensor] = None,
             rows_per_group: int = 0) -> torch.Tensor:
     """x: NHWC [n, h, w, cin]; w_packed: [cout, 9*cin] ([cout][kh][kw][cin]); out: [n*h*w, cout]."""
     n, h, w_, cin = x.shape
-    assert x.stride(3) == 1 and x.stride(1) == w_ * x.stride(2) and x.stride(0) == h * x.stride(1)
+    assert x.is_contiguous() or (x.stride(3) == 1 and x.stride(1) == w_ * x.stride(2) and x.stride(0) == h * x.stride(1))
     p = lib.GemmParams()
     p.dtype = lib.dtype_code(x.dtype)
     p.M, p.N, p.K = n * h * w_, w_packed.shape[0], w_packed.shape[1]
     assert p.K == 9 * cin
-    p.A, p.lda = lib.ptr(x), x.stride(2)
+    p.A, p.lda = lib.ptr(x), (cin if x.is_contiguous() else x.stride(2))
     p.W, p.ldw = lib.ptr(w_packed), _rowmajor_ld(w_packed)
     p.C, p.ldc = lib.ptr(out), _rowmajor_ld(out)
     p.bias = lib.ptr(bias)
@@ -90,6 +114,7 @@ def pack_geglu_weight(w: torch.Tensor, b: Optional[torch.Tensor]):
     return wi, bi
 
 
+@_timed(lambda q, k, v, out, **kw: f"attention C{q.shape[1]} L{kw['L']} rows{q.shape[0]}" + (" +ref" if kw.get("ref_index") is not None else ""))
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, L: int,
               kref: Optional[torch.Tensor] = None, vref: Optional[torch.Tensor] = None,
               ref_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -119,6 +144,7 @@ def _i(v) -> C.c_int:
     return C.c_int(int(v))
 
 
+@_timed(lambda x, *a, **kw: f"layernorm C{x.shape[1]} rows{x.shape[0]}")
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, *, eps: float = 1e-5,
               pe: Optional[torch.Tensor] = None, pe_index: Optional[torch.Tensor] = None, tokens_per_frame: int = 0,
               frames: int = 0) -> torch.Tensor:
@@ -133,6 +159,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
     return out
 
 
+@_timed(lambda x1, *a, **kw: f"groupnorm C{x1.shape[1] + (0 if kw.get('x2') is None else kw['x2'].shape[1])} rows{x1.shape[0]}")
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, stats_ws: torch.Tensor, *,
               n_frames: int, hw: int, groups: int = 32, eps: float = 1e-5, silu: bool = False,
               x2: Optional[torch.Tensor] = None, fpb_in: int = 0, fpb_out: int = 0, frame_off: int = 0) -> torch.Tensor:
@@ -149,6 +176,7 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: to
     return out
 
 
+@_timed(lambda q, *a, **kw: f"cross_attention keys{kw['n_keys']} d{kw['head_dim']} rows{q.shape[0]}")
 def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, frames: int, tokens: int,
                     heads: int, head_dim: int, n_keys: int, kv_frame_div: int = 1, regions: int = 1,
                     q_region_stride: int = 0, kv_region_stride: int = 0, o_region_stride: int = 0) -> torch.Tensor:
@@ -162,6 +190,7 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torc
     return out
 
 
+@_timed(lambda q, *a, **kw: f"temporal_attention C{q.shape[1]//3 if False else a[2].shape[1]} rows{q.shape[0]}")
 def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, batch: int, fq: int,
                        fk: int, tokens: int, heads: int) -> torch.Tensor:
     """q/out: [batch*fq*tokens, ld]; k/v: [batch*fk*tokens, ldkv]."""
@@ -174,6 +203,7 @@ def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     return out
 
 
+@_timed(lambda x, *a, **kw: f"upsample2x C{x.shape[3]} {x.shape[1]}")
 def upsample2x(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     assert x.is_contiguous() and out.is_contiguous() and out.numel() == 4 * x.numel()
@@ -183,6 +213,7 @@ def upsample2x(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_timed(lambda x, *a, **kw: f"phase_split C{x.shape[3]} {x.shape[1]}")
 def phase_split(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     assert x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
@@ -192,6 +223,7 @@ def phase_split(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_timed(lambda x, w, *a, **kw: f"conv3x3s2 {x.shape[3]}->{w.shape[0]} {kw['ho']}")
 def conv3x3_stride2(x_planes: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor, *, n: int, ho: int, wo: int,
                     bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x_planes: phase planes [4*n, ho, wo, cin] from phase_split; out: [n*ho*wo, cout]."""
@@ -212,16 +244,20 @@ def conv3x3_stride2(x_planes: torch.Tensor, w_packed: torch.Tensor, out: torch.T
     return out
 
 
+@_timed(lambda *a, **kw: "im2col_latent")
 def im2col_latent(latents: torch.Tensor, out: torch.Tensor, *, batch: int) -> torch.Tensor:
-    """latents: fp32 [1, Cl, F, H, W] contiguous; out: [batch*F*H*W, 64]."""
-    _, cl, f, h, w = latents.shape
+    """latents: fp32 [1 or batch, Cl, F, H, W] contiguous; out: [batch*F*H*W, 64]."""
+    lb, cl, f, h, w = latents.shape
     assert latents.dtype == torch.float32 and latents.is_contiguous() and out.is_contiguous()
+    assert lb in (1, batch)
     lib.check(lib.load().hallo_b200_im2col_latent(_i(lib.dtype_code(out.dtype)), C.c_void_p(lib.ptr(latents)),
                                                   C.c_void_p(lib.ptr(out)), _i(batch), _i(cl), _i(f), _i(h), _i(w),
+                                                  _i(1 if (lb == batch and batch > 1) else 0),
                                                   lib.current_stream()), "im2col_latent")
     return out
 
 
+@_timed(lambda *a, **kw: "timestep_embed")
 def timestep_embed(t_table: torch.Tensor, step: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     rows, dim = out.shape
     assert t_table.dtype == torch.float32 and step.dtype == torch.int32 and out.is_contiguous()
@@ -231,6 +267,7 @@ def timestep_embed(t_table: torch.Tensor, step: torch.Tensor, out: torch.Tensor)
     return out
 
 
+@_timed(lambda *a, **kw: "cfg_ddim_step")
 def cfg_ddim_step(model_out: torch.Tensor, latents: torch.Tensor, coef: torch.Tensor, step: torch.Tensor, *,
                   guidance: float, v_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """model_out: [2*F*HW, ld] tokens (uncond rows then cond rows); latents: fp32 [1, Cl, F, H, W] updated in place."""
@@ -248,6 +285,7 @@ def advance_step(step: torch.Tensor, n_steps: int) -> None:
               "advance_step")
 
 
+@_timed(lambda *a, **kw: "tokens_to_bcfhw")
 def tokens_to_bcfhw(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """x: [B*F*HW, ld] tokens (first C columns used); out: fp32 [B, C, F, H, W]."""
     b, c, f, h, w = out.shape

@@ -1,0 +1,71 @@
+"""DDIM schedule as the reference configures it: linear betas 0.00085 -> 0.012, zero-terminal-SNR
+rescale, trailing timestep spacing, v-prediction, eta 0, final_alpha_cumprod = 1
+(configs/inference/default.yaml:79-88, scripts/inference.py:186-193, hallo/animate/face_animate.py:285-286, 420).
+
+Only the per-step scalar tables live here (host side, fp64 -> fp32); the update itself is the
+`hallo_b200_cfg_ddim_step` kernel.  Mirrors the constructor keywords of diffusers.DDIMScheduler that the
+reference passes, so `DDIMScheduler(**sched_kwargs)` keeps working at the call site.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+
+class DDIMScheduler:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "linear", clip_sample: bool = False, set_alpha_to_one: bool = True,
+                 steps_offset: int = 1, prediction_type: str = "v_prediction", rescale_betas_zero_snr: bool = True,
+                 timestep_spacing: str = "trailing", **unused):
+        if beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        if prediction_type != "v_prediction" or clip_sample:
+            raise NotImplementedError("the Hallo pipeline uses v_prediction without clipping")
+        if rescale_betas_zero_snr:
+            abar_sqrt = torch.cumprod(1.0 - betas, 0).sqrt()
+            s0, sT = abar_sqrt[0].clone(), abar_sqrt[-1].clone()
+            abar_sqrt = (abar_sqrt - sT) * s0 / (s0 - sT)
+            abar = abar_sqrt ** 2
+            alphas = torch.cat([abar[0:1], abar[1:] / abar[:-1]])
+            betas = 1 - alphas
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, 0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_train_timesteps = num_train_timesteps
+        self.timestep_spacing = timestep_spacing
+        self.steps_offset = steps_offset
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = num_inference_steps
+        n, T = num_inference_steps, self.num_train_timesteps
+        if self.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)) - 1
+        elif self.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].copy() + self.steps_offset
+        else:
+            raise NotImplementedError(self.timestep_spacing)
+        self.timesteps = torch.from_numpy(ts.astype(np.int64)).to(device)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def coef_table(self) -> torch.Tensor:
+        """[n_steps, 4] = sqrt(a_t), sqrt(1 - a_t), sqrt(a_prev), sqrt(1 - a_prev) per inference step."""
+        n = self.num_inference_steps
+        rows: List[List[float]] = []
+        for t in self.timesteps.tolist():
+            prev = t - self.num_train_timesteps // n
+            a_t = self.alphas_cumprod[t].double()
+            a_p = self.alphas_cumprod[prev].double() if prev >= 0 else self.final_alpha_cumprod.double()
+            rows.append([float(a_t.sqrt()), float((1 - a_t).sqrt()), float(a_p.sqrt()), float((1 - a_p).sqrt())])
+        return torch.tensor(rows, dtype=torch.float32)

@@ -99,3 +99,19 @@ def synth_inputs(cfg: UNetConfig, h: int, w: int, f: int, seed: int = 42, dtype=
                full_mask=[m.to(dtype) for m in masks["full"]], face_mask=[m.to(dtype) for m in masks["face"]],
                lip_mask=[m.to(dtype) for m in masks["lip"]], motion_scale=list(motion_scale), banks=banks)
     return out
+
+
+def host_threads() -> int:
+    """Usable host cores: the scheduler affinity mask (cgroup-limited boxes report the whole host in cpu_count)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(int(q[0]) / int(q[1]))))
+    except Exception:
+        pass
+    return max(1, n)

@@ -182,9 +182,11 @@ int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t ldq, const v
 int hallo_b200_upsample2x(int dtype, const void* x, void* out, int N, int H, int W, int C, hb_stream_t stream);
 /* space-to-depth phase planes feeding the stride-2 conv (conv3x3 == 2). */
 int hallo_b200_phase_split(int dtype, const void* x, void* out, int N, int H, int W, int C, hb_stream_t stream);
-/* im2col of the fp32 latents [1, Cl, F, H, W] for conv_in (unet_3d.py:603): out [batch*F*H*W, 64]. */
+/* im2col of the fp32 latents for conv_in (unet_3d.py:603): out [batch*F*H*W, 64].  latents are
+ * [1, Cl, F, H, W] shared by both CFG halves (face_animate.py:398) or, with per_half_latents != 0,
+ * [batch, Cl, F, H, W]. */
 int hallo_b200_im2col_latent(int dtype, const float* latents, void* out, int batch, int Cl, int F, int H,
-                             int W, hb_stream_t stream);
+                             int W, int per_half_latents, hb_stream_t stream);
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, shift 0) for t = t_table[*step] (unet_3d.py:565-587). */
 int hallo_b200_timestep_embed(int dtype, const float* t_table, const int32_t* step, void* out, int rows,
                               int dim, hb_stream_t stream);

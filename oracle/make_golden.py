@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from hallo_b200.spec import UNetConfig  # noqa: E402
-from hallo_b200.synth import synth_inputs, synth_state_dict  # noqa: E402
+from hallo_b200.synth import host_threads, synth_inputs, synth_state_dict  # noqa: E402
 from oracle import ref_host  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -34,7 +34,7 @@ def checksum(t: torch.Tensor) -> float:
 
 
 def main():
-    torch.set_num_threads(os.cpu_count() or 8)
+    torch.set_num_threads(host_threads())
     os.makedirs(GOLD, exist_ok=True)
     cfg = UNetConfig()
     unet = ref_host.build_reference_unet()

@@ -82,7 +82,8 @@ def test_gemm_geglu_and_split_k():
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 64, 320, 320), (4, 32, 32, 640, 320), (4, 16, 16, 1280, 640),
-                                            (4, 8, 8, 1280, 1280), (2, 24, 24, 128, 160), (8, 12, 12, 64, 160)])
+                                            (4, 8, 8, 1280, 1280), (2, 24, 24, 128, 160), (8, 12, 12, 64, 160),
+                                            (4, 1, 1, 320, 320), (6, 2, 2, 640, 160), (3, 20, 12, 64, 320)])
 def test_conv3x3(n, h, w, cin, cout):
     from hallo_b200 import ops
     dev = _dev()

@@ -1,0 +1,123 @@
+"""CPU tests of the host-side logic: C-ABI surface, weight packing, scheduler tables, shard planning and the
+world_size-2 gloo path of the temporal K/V gather."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "hallo_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(hallo_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    lib = ctypes.CDLL(os.path.join(ROOT, "hallo_b200", "libhallo_b200.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.hallo_b200_abi_version.restype = ctypes.c_int
+    assert lib.hallo_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product must fail loudly without CUDA, and must not import the oracle."""
+    from hallo_b200.models.unet_3d import UNet3DConditionModel
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hallo_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+    if not torch.cuda.is_available():
+        from hallo_b200.spec import HALLO_UNET_KWARGS, SD15_UNET_CONFIG
+        tiny = dict(SD15_UNET_CONFIG)
+        m = UNet3DConditionModel.from_config(tiny, **HALLO_UNET_KWARGS)
+        m.set_banks({"x": torch.zeros(1)})
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(2, 4, 1, 8, 8), 1, torch.zeros(2, 4, 768), audio_embedding=torch.zeros(2, 1, 32, 768),
+              mask_cond_fea=None, full_mask=[torch.zeros(2, 64)], face_mask=[torch.zeros(2, 64)],
+              lip_mask=[torch.zeros(2, 64)])
+
+
+def test_weight_packing_layouts():
+    from hallo_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(16, 8, 3, 3, generator=g)
+    x = torch.randn(2, 8, 5, 5, generator=g)
+    wp = ops.pack_conv3x3_weight(w)                                   # [cout, (kh kw cin)]
+    cols = F.unfold(x, 3, padding=1).view(2, 8, 9, 25).permute(0, 3, 2, 1).reshape(50, 72)   # (tap, cin) order
+    ref = F.conv2d(x, w, padding=1).permute(0, 2, 3, 1).reshape(50, 16)
+    assert torch.allclose(cols @ wp.t(), ref, atol=1e-4)
+    w1 = torch.randn(32, 4, generator=g)
+    b1 = torch.randn(32, generator=g)
+    wi, bi = ops.pack_geglu_weight(w1, b1)
+    h = torch.randn(3, 4, generator=g)
+    full = h @ w1.t() + b1
+    inter = h @ wi.t() + bi
+    assert torch.allclose(inter[:, 0::2], full[:, :16]) and torch.allclose(inter[:, 1::2], full[:, 16:])
+
+
+def test_scheduler_tables():
+    from hallo_b200.scheduler import DDIMScheduler
+    s = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                      prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    s.set_timesteps(40)
+    assert s.timesteps.tolist()[:2] == [999, 974] and s.timesteps.tolist()[-1] == 24
+    c = s.coef_table()
+    assert c.shape == (40, 4) and abs(float(c[0, 0])) < 1e-6 and abs(float(c[-1, 2]) - 1.0) < 1e-7
+    assert torch.allclose(c[:, 0] ** 2 + c[:, 1] ** 2, torch.ones(40), atol=1e-6)
+    assert torch.allclose(c[1:, 0], c[:-1, 2], atol=1e-6)            # a_prev of step i == a_t of step i+1
+
+
+def test_shard_layout():
+    from hallo_b200.dist import shard_layout
+    for world in (1, 2, 4, 8):
+        lay = shard_layout(world, 16)
+        rows = sorted((b, g) for halves, frames in lay for b in halves for g in frames)
+        assert rows == [(b, g) for b in (0, 1) for g in range(16)]    # every (half, frame) owned exactly once
+    with pytest.raises(ValueError):
+        shard_layout(3, 16)
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HB_ROOT"])
+from hallo_b200.dist import plan_shard, gather_temporal_kv
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_frames, nm, L, C2 = 8, 2, 3, 4
+# 4 "virtual" ranks cannot run here; world=2 => one rank per CFG half, group_size 1: the gather degenerates.
+sh = plan_shard(rank, world, n_frames)
+assert sh.halves == (rank,) and sh.frames == tuple(range(n_frames)) and sh.group_size == 1
+# exercise the gather collective itself with a 2-rank frame group (the code path ranks of one CFG half use)
+g = dist.new_group([0, 1])
+fl = n_frames // 2
+glob = torch.arange((nm + n_frames) * L * C2, dtype=torch.float32).reshape(nm + n_frames, L, C2)
+local = glob[nm + rank * fl: nm + (rank + 1) * fl]
+full = gather_temporal_kv(local, glob[:nm], g, 2)
+assert torch.equal(full, glob), (rank, full.flatten()[:8])
+# CFG-combine exchange layout (engine._step_tail): all_gather over world, uncond group first
+mo = torch.full((5, 8), float(rank))
+allm = torch.empty(world * 5, 8)
+dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1))
+assert float(allm[:5].mean()) == 0.0 and float(allm[5:].mean()) == 1.0
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_temporal_gather(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, HB_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

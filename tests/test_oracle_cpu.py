@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from conftest import rel_l2
 from hallo_b200.spec import UNetConfig, build_blocks, param_spec, reader_bank_order
-from hallo_b200.synth import synth_inputs, synth_state_dict
+from hallo_b200.synth import host_threads, synth_inputs, synth_state_dict
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -22,7 +22,7 @@ def cfg():
 
 @pytest.fixture(scope="module")
 def sd(cfg):
-    torch.set_num_threads(os.cpu_count() or 8)
+    torch.set_num_threads(host_threads())
     return synth_state_dict(cfg, seed=0)
 
 
