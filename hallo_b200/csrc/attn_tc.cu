@@ -374,28 +374,4 @@ static int launch_attn(const hb_attention_params* q, cudaStream_t stream) {
   return HB_OK;
 }
 
-template <typename T>
-static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
-  switch (p->head_dim) {
-    case 40: return launch_attn<T, 40, 128, 2>(p, s);
-    case 80: return launch_attn<T, 80, 64, 2>(p, s);
-    case 160: return launch_attn<T, 160, 64, 2>(p, s);
-    default: return fail(HB_ERR_BAD_SHAPE, "attention: head_dim %d not in {40, 80, 160}", p->head_dim);
-  }
-}
-
 }  // namespace hb
-
-extern "C" int hallo_b200_attention(const hb_attention_params* p, hb_stream_t stream) {
-  using namespace hb;
-  if (p == nullptr || p->Q == nullptr || p->K == nullptr || p->V == nullptr || p->O == nullptr)
-    return fail(HB_ERR_NULL, "hallo_b200_attention: null pointer");
-  if (p->L <= 0 || p->frames <= 0 || p->heads <= 0 || p->heads > 256)
-    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_attention: L=%d frames=%d heads=%d", p->L, p->frames, p->heads);
-  if (p->ldq % 8 || p->ldk % 8 || p->ldv % 8 || p->ldo % 8)
-    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_attention: leading dims must be multiples of 8");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (p->dtype == HB_F16) return dispatch_attn<__half>(p, s);
-  if (p->dtype == HB_BF16) return dispatch_attn<__nv_bfloat16>(p, s);
-  return fail(HB_ERR_BAD_DTYPE, "hallo_b200_attention: dtype %d", p->dtype);
-}

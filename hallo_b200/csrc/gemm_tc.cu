@@ -17,6 +17,14 @@ namespace hb {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 192;
+constexpr int kStgStride = 80;   // bytes per staged row: 64 B of data + 16 B pad (conflict-free 128-bit access)
+
+template <typename T>
+__device__ __forceinline__ void load8g(const T* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = Cvt<T>::unpack2(u.x), b = Cvt<T>::unpack2(u.y), c = Cvt<T>::unpack2(u.z), d = Cvt<T>::unpack2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
 
 struct GemmDev {
   int M, N, K, K1;
@@ -42,7 +50,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kStgOffset = kBarOffset + 256;
+  static constexpr int kTotal = kStgOffset + 4 * 2 * 32 * 80 + 1024;  // + barriers + epilogue staging + slack
 };
 
 template <typename T, int BN, int STAGES, bool CONV>
@@ -187,6 +196,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const T* resid = reinterpret_cast<const T*>(p.residual);
     T* C = reinterpret_cast<T*>(p.C);
     const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    uint8_t* stg = smem + SM::kStgOffset + (warp - 2) * (2 * 32 * kStgStride);   // per-warp [32][80 B] output chunk
+    uint8_t* rsd = stg + 32 * kStgStride;                                          // per-warp residual chunk
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tm = t / p.tiles_n;
@@ -217,98 +228,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (rscale != nullptr && row_ok) rs *= Cvt<T>::to_f(rscale[row]);
       const T* gb_row = nullptr;
       if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
+      // rows owned by the other lanes of this warp (for the coalesced global phases)
+      long long crow[4];
+      bool cok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        crow[i] = __shfl_sync(0xffffffffu, row, r);
+        cok[i] = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
+      }
+      const int n_out = geglu ? (p.N >> 1) : p.N;
+      const int cunit = lane & 3;                       // 16-byte unit inside a 32-column chunk
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
+      uint32_t racc[2][32];
+      tmem_ld_x32(taddr, racc[0]);
+      tmem_ld_wait();
+#pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_x32(taddr + c * 32, r);
-        tmem_ld_wait();
+        uint32_t(&r)[32] = racc[c & 1];
+        if (c + 1 < BN / 32) tmem_ld_x32(taddr + (c + 1) * 32, racc[(c + 1) & 1]);   // overlaps with this chunk's math
         const int col0 = tn * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-        float v[32];
+        const int ocol0 = geglu ? (col0 >> 1) : col0;    // first output column of this chunk
+        const int ounits = geglu ? 2 : 4;                // 16-byte units of output per row in this chunk
+        const bool chunk_ok = col0 < p.N;
+        // ---- residual: coalesced global -> smem (each row's slice is read as contiguous 16-byte units) ----
+        if (resid != nullptr && chunk_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              uint4 b4 = *reinterpret_cast<const uint4*>(bias + col0 + j);
-              float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
-                     f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
-              v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
-              v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+          for (int i = 0; i < 4; ++i) {
+            if (cunit < ounits && cok[i] && ocol0 + cunit * 8 < n_out) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(resid + crow[i] * p.ldr + ocol0 + cunit * 8);
+              *reinterpret_cast<uint4*>(rsd + (i * 8 + (lane >> 2)) * kStgStride + cunit * 16) = v4;
             }
           }
         }
-        if (gb_row != nullptr) {
+        __syncwarp();
+        if (chunk_ok) {
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              uint4 b4 = *reinterpret_cast<const uint4*>(gb_row + col0 + j);
-              float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
-                     f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
-              v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
-              v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.N) {
+                float f[8];
+                load8g(bias + col0 + j, f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[j + q] += f[q];
+              }
             }
           }
-        }
-        if (p.flags & HB_EPI_SILU) {
+          if (gb_row != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-        }
-        if (geglu) {
-          // columns come as (value, gate) pairs; 32 accumulator columns -> 16 outputs
-          const int ocol0 = col0 >> 1;
-          float o[16];
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.N) {
+                float f[8];
+                load8g(gb_row + col0 + j, f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]) * rs;
-          T* dst = C + row * p.ldc + ocol0;
-          if (resid != nullptr) {
-            const T* rp = resid + row * p.ldr + ocol0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += Cvt<T>::to_f(rp[j]);
+                for (int q = 0; q < 8; ++q) v[j + q] += f[q];
+              }
+            }
           }
+          if (p.flags & HB_EPI_SILU) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            if (col0 + 2 * j < p.N) {
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+          uint8_t* my_rsd = rsd + lane * kStgStride;
+          uint8_t* my_stg = stg + lane * kStgStride;
+          if (geglu) {
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]) * rs;
+            if (resid != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                float f[8];
+                load8g(reinterpret_cast<const T*>(my_rsd) + j, f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[j + q] += f[q];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
               uint4 o4;
               o4.x = Cvt<T>::pack2(o[j + 0], o[j + 1]);
               o4.y = Cvt<T>::pack2(o[j + 2], o[j + 3]);
               o4.z = Cvt<T>::pack2(o[j + 4], o[j + 5]);
               o4.w = Cvt<T>::pack2(o[j + 6], o[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = o4;
+              *reinterpret_cast<uint4*>(my_stg + j * 2) = o4;
             }
-          }
-        } else {
-          T* dst = C + row * p.ldc + col0;
-          const T* rp = resid != nullptr ? resid + row * p.ldr + col0 : nullptr;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
+            for (int j = 0; j < 32; j += 8) {
               float w[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) w[q] = v[j + q] * rs;
-              if (rp != nullptr) {
-                uint4 b4 = *reinterpret_cast<const uint4*>(rp + j);
-                float2 f0 = Cvt<T>::unpack2(b4.x), f1 = Cvt<T>::unpack2(b4.y),
-                       f2 = Cvt<T>::unpack2(b4.z), f3 = Cvt<T>::unpack2(b4.w);
-                w[0] += f0.x; w[1] += f0.y; w[2] += f1.x; w[3] += f1.y;
-                w[4] += f2.x; w[5] += f2.y; w[6] += f3.x; w[7] += f3.y;
+              if (resid != nullptr) {
+                float f[8];
+                load8g(reinterpret_cast<const T*>(my_rsd) + j, f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] += f[q];
               }
               uint4 o4;
               o4.x = Cvt<T>::pack2(w[0], w[1]);
               o4.y = Cvt<T>::pack2(w[2], w[3]);
               o4.z = Cvt<T>::pack2(w[4], w[5]);
               o4.w = Cvt<T>::pack2(w[6], w[7]);
-              *reinterpret_cast<uint4*>(dst + j) = o4;
+              *reinterpret_cast<uint4*>(my_stg + j * 2) = o4;
             }
           }
         }
-        }  // row_ok
+        __syncwarp();
+        // ---- output: smem -> coalesced global stores ----
+        if (chunk_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (cunit < ounits && cok[i] && ocol0 + cunit * 8 < n_out) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + (i * 8 + (lane >> 2)) * kStgStride + cunit * 16);
+              *reinterpret_cast<uint4*>(C + crow[i] * p.ldc + ocol0 + cunit * 8) = v4;
+            }
+          }
+        }
+        if (c + 1 < BN / 32) tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();

@@ -3,6 +3,8 @@
 #include "host_common.cu"
 #include "gemm_tc.cu"
 #include "attn_tc.cu"
+#include "attn2_tc.cu"
+#include "attn_api.cu"
 #include "aux.cu"
 
 extern "C" int hallo_b200_device_error(unsigned int* code_out) {
