@@ -32,7 +32,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // LayerNorm over C (one warp per row), optional sinusoidal positional-encoding add after the norm
 // (motion_module.py:585-586: PE is added to LN(x) before q/k/v).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MAXV>
+template <typename T, int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, long long ldx,
                                                         T* __restrict__ out, long long ldo,
                                                         const T* __restrict__ gamma,
@@ -40,59 +40,62 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                                                         float eps, const float* __restrict__ pe,
                                                         const int* __restrict__ pe_index, int L,
                                                         int frames) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // LPR lanes cooperate on one row (C = LPR * VPL * 8 channels); a warp handles 32 / LPR rows.
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
-  const int nvec = C >> 3;
-  float v[MAXV][8];
+  const int sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  float v[VPL][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      load8(x + (long long)row * ldx + vi * 8, v[i]);
+  for (int i = 0; i < VPL; ++i) {
+    if (ok) {
+      load8(x + row * ldx + (sub + i * LPR) * 8, v[i]);
+    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
   }
-  const float mean = warp_sum(s) / C;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+  for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        ss += d * d;
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      ss += d * d;
     }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / C + eps);
+  if (!ok) return;
   const float* perow = nullptr;
   if (pe != nullptr) {
-    int f = (row / L) % frames;
+    int f = (int)((row / L) % frames);
     if (pe_index != nullptr) f = pe_index[f];
     perow = pe + (long long)f * C;
   }
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float g[8], b[8], o[8];
-      load8(gamma + vi * 8, g);
-      load8(beta + vi * 8, b);
+  for (int i = 0; i < VPL; ++i) {
+    const int c0 = (sub + i * LPR) * 8;
+    float g[8], b[8], o[8];
+    load8(gamma + c0, g);
+    load8(beta + c0, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = (v[i][j] - mean) * rstd * g[j] + b[j];
-        if (perow != nullptr) {
-          // the reference adds PE to the (already rounded) LN output in the model dtype
-          y = Cvt<T>::to_f(Cvt<T>::from_f(y)) + perow[vi * 8 + j];
-        }
-        o[j] = y;
+    for (int j = 0; j < 8; ++j) {
+      float y = (v[i][j] - mean) * rstd * g[j] + b[j];
+      if (perow != nullptr) {
+        // the reference adds PE to the (already rounded) LN output in the model dtype
+        y = Cvt<T>::to_f(Cvt<T>::from_f(y)) + perow[c0 + j];
       }
-      store8(out + (long long)row * ldo + vi * 8, o);
+      o[j] = y;
     }
+    store8(out + row * ldo + c0, o);
   }
 }
 
@@ -154,51 +157,60 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x1,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x1, int C1,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1, int C1,
                                                        const T* __restrict__ x2, int C2, int HW,
-                                                       int G, const float* __restrict__ stats,
+                                                       int pix_per_cta, int G,
+                                                       const float* __restrict__ stats,
                                                        const T* __restrict__ gamma,
                                                        const T* __restrict__ beta, float eps,
                                                        int silu, T* __restrict__ out, int fpb_in,
                                                        int fpb_out, int frame_off) {
-  __shared__ float s_mean[64], s_rstd[64];
+  // thread (cv, py): fixed 8 channels, strided pixels -> per-channel scale/shift live in registers
   const int C = C1 + C2;
   const int nvec = C >> 3;
+  const int PY = blockDim.x / nvec;
+  const int cv = threadIdx.x % nvec;
+  const int py = threadIdx.x / nvec;
+  if (py >= PY) return;
   const int n = blockIdx.y;
   const int cpg = C / G;
-  if (threadIdx.x < G) {
-    const float cnt = (float)cpg * HW;
-    const float m = stats[((long long)n * G + threadIdx.x) * 2] / cnt;
-    const float var = fmaxf(stats[((long long)n * G + threadIdx.x) * 2 + 1] / cnt - m * m, 0.f);
-    s_mean[threadIdx.x] = m;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
-  }
-  __syncthreads();
-  const int n_out = (n / fpb_in) * fpb_out + frame_off + (n % fpb_in);
-  const long long total = (long long)HW * nvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i / nvec);
-    const int cv = (int)(i - (long long)p * nvec);
-    const int c0 = cv * 8;
-    float v[8], g[8], b[8], o[8];
-    if (c0 < C1)
-      load8(x1 + ((long long)n * HW + p) * C1 + c0, v);
-    else
-      load8(x2 + ((long long)n * HW + p) * C2 + (c0 - C1), v);
+  const int c0 = cv * 8;
+  float sc[8], sh[8];
+  {
+    float g[8], b[8];
     load8(gamma + c0, g);
     load8(beta + c0, b);
+    const float cnt = (float)cpg * HW;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / cpg;
-      float y = (v[j] - s_mean[grp]) * s_rstd[grp] * g[j] + b[j];
+      const float m = stats[((long long)n * G + grp) * 2] / cnt;
+      const float var = fmaxf(stats[((long long)n * G + grp) * 2 + 1] / cnt - m * m, 0.f);
+      const float r = rsqrtf(var + eps);
+      sc[j] = r * g[j];
+      sh[j] = b[j] - m * r * g[j];
+    }
+  }
+  const int n_out = (n / fpb_in) * fpb_out + frame_off + (n % fpb_in);
+  const bool first = c0 < C1;
+  const T* src = first ? x1 + (long long)n * HW * C1 + c0 : x2 + (long long)n * HW * C2 + (c0 - C1);
+  const int ld = first ? C1 : C2;
+  T* dst = out + (long long)n_out * HW * C + c0;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int p = p0 + py; p < p1; p += PY) {
+    float v[8], o[8];
+    load8(src + (long long)p * ld, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(v[j], sc[j], sh[j]);
       if (silu) {
-        y = Cvt<T>::to_f(Cvt<T>::from_f(y));   // reference rounds GN output before SiLU
+        y = Cvt<T>::to_f(Cvt<T>::from_f(y));   // reference rounds the GN output before SiLU
         y = silu_f(y);
       }
       o[j] = y;
     }
-    store8(out + ((long long)n_out * HW + p) * C + c0, o);
+    store8(dst + (long long)p * C, o);
   }
 }
 
@@ -277,21 +289,23 @@ __global__ void __launch_bounds__(128) xattn_kernel(
 // One thread per (batch, query frame, pixel, head); keys / values stream through L1.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MAXF>
-__global__ void __launch_bounds__(128) tattn_kernel(const T* __restrict__ Q, long long ldq,
+__global__ void __launch_bounds__(288) tattn_kernel(const T* __restrict__ Q, long long ldq,
                                                     const T* __restrict__ K,
                                                     const T* __restrict__ V, long long ldkv,
                                                     T* __restrict__ O, long long ldo, int batch,
                                                     int Fq, int Fk, int L, int heads, int d,
                                                     float scale_log2) {
+  // thread order (head, query frame, pixel, batch): the Fq query frames of a pixel sit next to each other,
+  // so the 2*Fk K/V rows of that pixel are fetched from L2 once and re-read by the other frames through L1.
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)batch * Fq * L * heads;
   if (idx >= total) return;
   const int head = (int)(idx % heads);
   long long t = idx / heads;
-  const int pix = (int)(t % L);
-  t /= L;
   const int fq = (int)(t % Fq);
-  const int b = (int)(t / Fq);
+  t /= Fq;
+  const int pix = (int)(t % L);
+  const int b = (int)(t / L);
   const T* q = Q + (((long long)b * Fq + fq) * L + pix) * ldq + head * d;
   const T* kbase = K + ((long long)b * Fk * L + pix) * ldkv + head * d;
   const T* vbase = V + ((long long)b * Fk * L + pix) * ldkv + head * d;
@@ -525,20 +539,29 @@ extern "C" int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void*
                                     const float* pe, const int32_t* pe_index, int L, int frames,
                                     hb_stream_t stream) {
   if (!x || !out || !gamma || !beta) return fail(HB_ERR_NULL, "layernorm: null pointer");
-  if (C % 8 != 0 || C > 2560 || ldx % 8 || ldo % 8) return fail(HB_ERR_BAD_SHAPE, "layernorm: C=%d", C);
+  if (C % 8 != 0 || ldx % 8 || ldo % 8) return fail(HB_ERR_BAD_SHAPE, "layernorm: C=%d", C);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
-  const int grid = (rows + wpb - 1) / wpb;
+#define HB_LN_LAUNCH(LPR, VPL)                                                                          \
+  {                                                                                                     \
+    const int rpb = wpb * (32 / LPR);                                                                   \
+    const int grid = (rows + rpb - 1) / rpb;                                                            \
+    layernorm_kernel<T, LPR, VPL><<<grid, wpb * 32, 0, s>>>((const T*)x, ldx, (T*)out, ldo,             \
+                                                             (const T*)gamma, (const T*)beta, rows, C,  \
+                                                             eps, pe, pe_index, L > 0 ? L : 1,          \
+                                                             frames > 0 ? frames : 1);                  \
+  }
   HB_DISPATCH_T(dtype, {
-    if (C <= 1280)
-      layernorm_kernel<T, 5><<<grid, wpb * 32, 0, s>>>((const T*)x, ldx, (T*)out, ldo, (const T*)gamma,
-                                                        (const T*)beta, rows, C, eps, pe, pe_index,
-                                                        L > 0 ? L : 1, frames > 0 ? frames : 1);
-    else
-      layernorm_kernel<T, 10><<<grid, wpb * 32, 0, s>>>((const T*)x, ldx, (T*)out, ldo, (const T*)gamma,
-                                                         (const T*)beta, rows, C, eps, pe, pe_index,
-                                                         L > 0 ? L : 1, frames > 0 ? frames : 1);
+    switch (C) {
+      case 320: HB_LN_LAUNCH(8, 5) break;
+      case 640: HB_LN_LAUNCH(16, 5) break;
+      case 1280: HB_LN_LAUNCH(32, 5) break;
+      case 2560: HB_LN_LAUNCH(32, 10) break;
+      case 768: HB_LN_LAUNCH(32, 3) break;
+      default: return fail(HB_ERR_BAD_SHAPE, "layernorm: C=%d not in {320, 640, 768, 1280, 2560}", C);
+    }
   })
+#undef HB_LN_LAUNCH
   HB_LAUNCH_CHECK();
   return HB_OK;
 }
@@ -567,13 +590,12 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
     gn_stats_kernel<T><<<g1, threads, smem, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, pix_per_cta, G,
                                                  stats_ws);
     HB_LAUNCH_CHECK();
-    long long total = (long long)HW * nvec;
-    int gx = (int)((total + 256 * 4 - 1) / (256 * 4));
-    if (gx < 1) gx = 1;
-    dim3 g2(gx, N);
-    gn_apply_kernel<T><<<g2, 256, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, G, stats_ws,
-                                          (const T*)gamma, (const T*)beta, eps, silu, (T*)out, fpb_in,
-                                          fpb_out, frame_off);
+    int ppc = 64;                                     // pixels per CTA of the apply pass
+    if (HW < ppc) ppc = HW;
+    dim3 g2((HW + ppc - 1) / ppc, N);
+    gn_apply_kernel<T><<<g2, threads, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, ppc, G, stats_ws,
+                                              (const T*)gamma, (const T*)beta, eps, silu, (T*)out, fpb_in,
+                                              fpb_out, frame_off);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;
@@ -616,14 +638,15 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
     return fail(HB_ERR_BAD_SHAPE, "temporal_attention: head_dim=%d Fk=%d", head_dim, Fk);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)batch * Fq * L * heads;
-  const int grid = (int)((total + 127) / 128);
+  const int block = (heads * Fq <= 288 && (288 % (heads * Fq)) == 0) ? 288 : 256;   // whole pixels per CTA when possible
+  const int grid = (int)((total + block - 1) / block);
   const float sc = (float)(1.4426950408889634 / sqrt((double)head_dim));
   HB_DISPATCH_T(dtype, {
     if (Fk <= 18)
-      tattn_kernel<T, 18><<<grid, 128, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
+      tattn_kernel<T, 18><<<grid, block, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
                                                ldo, batch, Fq, Fk, L, heads, head_dim, sc);
     else
-      tattn_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
+      tattn_kernel<T, 32><<<grid, block, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
                                                ldo, batch, Fq, Fk, L, heads, head_dim, sc);
   })
   HB_LAUNCH_CHECK();

@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer  (A tile 128x64, W tile BNx64 per stage, 128B-swizzled)
 //   warp 1      : MMA issuer    (one elected lane; tcgen05.mma M=128, N=BN, K=16; fp32 in TMEM)
-//   warps 2..5  : epilogue      (tcgen05.ld -> bias / temb / GEGLU / mask / residual -> global)
+//   warps 2..9  : epilogue      (tcgen05.ld -> bias / temb / GEGLU / mask / residual -> global);
+//                 warp w drains TMEM lanes 32*(w%4).. and accumulator columns (w-2)/4 * BN/2 ..
 //
 // Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of tile i.
 // Tiles are walked n-fastest so the CTAs running concurrently share the same A rows in L2.
@@ -16,7 +17,7 @@ namespace hb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kStgStride = 80;   // bytes per staged row: 64 B of data + 16 B pad (conflict-free 128-bit access)
 
 template <typename T>
@@ -50,8 +51,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kStgOffset = kBarOffset + 256;
-  static constexpr int kTotal = kStgOffset + 4 * 2 * 32 * 80 + 1024;  // + barriers + epilogue staging + slack
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
 
 template <typename T, int BN, int STAGES, bool CONV>
@@ -86,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -196,8 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const T* resid = reinterpret_cast<const T*>(p.residual);
     T* C = reinterpret_cast<T*>(p.C);
     const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
-    uint8_t* stg = smem + SM::kStgOffset + (warp - 2) * (2 * 32 * kStgStride);   // per-warp [32][80 B] output chunk
-    uint8_t* rsd = stg + 32 * kStgStride;                                          // per-warp residual chunk
+    const int chalf = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tm = t / p.tiles_n;
@@ -228,50 +227,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (rscale != nullptr && row_ok) rs *= Cvt<T>::to_f(rscale[row]);
       const T* gb_row = nullptr;
       if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
-      // rows owned by the other lanes of this warp (for the coalesced global phases)
-      long long crow[4];
-      bool cok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = i * 8 + (lane >> 2);
-        crow[i] = __shfl_sync(0xffffffffu, row, r);
-        cok[i] = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
-      }
       const int n_out = geglu ? (p.N >> 1) : p.N;
-      const int cunit = lane & 3;                       // 16-byte unit inside a 32-column chunk
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
-      uint32_t racc[2][32];
-      tmem_ld_x32(taddr, racc[0]);
+      // this warp owns TMEM lanes [32*quarter, +32) and accumulator columns [chalf*BN/2, +BN/2), 16 at a time
+      const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
+      constexpr int kChunks = BN / 2 / 16;
+      uint32_t racc[2][16];
+      tmem_ld_x16(taddr, racc[0]);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t(&r)[32] = racc[c & 1];
-        if (c + 1 < BN / 32) tmem_ld_x32(taddr + (c + 1) * 32, racc[(c + 1) & 1]);   // overlaps with this chunk's math
-        const int col0 = tn * BN + c * 32;
-        const int ocol0 = geglu ? (col0 >> 1) : col0;    // first output column of this chunk
-        const int ounits = geglu ? 2 : 4;                // 16-byte units of output per row in this chunk
-        const bool chunk_ok = col0 < p.N;
-        // ---- residual: coalesced global -> smem (each row's slice is read as contiguous 16-byte units) ----
-        if (resid != nullptr && chunk_ok) {
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t(&r)[16] = racc[c & 1];
+        if (c + 1 < kChunks) tmem_ld_x16(taddr + (c + 1) * 16, racc[(c + 1) & 1]);   // overlaps with this chunk's math
+        const int col0 = tn * BN + chalf * (BN / 2) + c * 16;
+        if (row_ok && col0 < p.N) {
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (cunit < ounits && cok[i] && ocol0 + cunit * 8 < n_out) {
-              const uint4 v4 = *reinterpret_cast<const uint4*>(resid + crow[i] * p.ldr + ocol0 + cunit * 8);
-              *reinterpret_cast<uint4*>(rsd + (i * 8 + (lane >> 2)) * kStgStride + cunit * 16) = v4;
-            }
-          }
-        }
-        __syncwarp();
-        if (chunk_ok) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 16; j += 8) {
               if (col0 + j < p.N) {
                 float f[8];
                 load8g(bias + col0 + j, f);
@@ -282,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (gb_row != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 16; j += 8) {
               if (col0 + j < p.N) {
                 float f[8];
                 load8g(gb_row + col0 + j, f);
@@ -293,65 +270,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.flags & HB_EPI_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
           }
-          uint8_t* my_rsd = rsd + lane * kStgStride;
-          uint8_t* my_stg = stg + lane * kStgStride;
           if (geglu) {
-            float o[16];
+            // (value, gate) pairs: 16 accumulator columns -> 8 outputs
+            const int ocol0 = col0 >> 1;
+            float o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]) * rs;
+            for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
             if (resid != nullptr) {
+              float f[8];
+              load8g(resid + row * p.ldr + ocol0, f);
 #pragma unroll
-              for (int j = 0; j < 16; j += 8) {
-                float f[8];
-                load8g(reinterpret_cast<const T*>(my_rsd) + j, f);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[j + q] += f[q];
-              }
+              for (int q = 0; q < 8; ++q) o[q] += f[q];
             }
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              uint4 o4;
-              o4.x = Cvt<T>::pack2(o[j + 0], o[j + 1]);
-              o4.y = Cvt<T>::pack2(o[j + 2], o[j + 3]);
-              o4.z = Cvt<T>::pack2(o[j + 4], o[j + 5]);
-              o4.w = Cvt<T>::pack2(o[j + 6], o[j + 7]);
-              *reinterpret_cast<uint4*>(my_stg + j * 2) = o4;
-            }
+            uint4 o4;
+            o4.x = Cvt<T>::pack2(o[0], o[1]);
+            o4.y = Cvt<T>::pack2(o[2], o[3]);
+            o4.z = Cvt<T>::pack2(o[4], o[5]);
+            o4.w = Cvt<T>::pack2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(C + row * p.ldc + ocol0) = o4;
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float w[8];
+            for (int j = 0; j < 16; j += 8) {
+              if (col0 + j < n_out) {
+                float w[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) w[q] = v[j + q] * rs;
-              if (resid != nullptr) {
-                float f[8];
-                load8g(reinterpret_cast<const T*>(my_rsd) + j, f);
+                for (int q = 0; q < 8; ++q) w[q] = v[j + q] * rs;
+                if (resid != nullptr) {
+                  float f[8];
+                  load8g(resid + row * p.ldr + col0 + j, f);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) w[q] += f[q];
+                  for (int q = 0; q < 8; ++q) w[q] += f[q];
+                }
+                uint4 o4;
+                o4.x = Cvt<T>::pack2(w[0], w[1]);
+                o4.y = Cvt<T>::pack2(w[2], w[3]);
+                o4.z = Cvt<T>::pack2(w[4], w[5]);
+                o4.w = Cvt<T>::pack2(w[6], w[7]);
+                *reinterpret_cast<uint4*>(C + row * p.ldc + col0 + j) = o4;
               }
-              uint4 o4;
-              o4.x = Cvt<T>::pack2(w[0], w[1]);
-              o4.y = Cvt<T>::pack2(w[2], w[3]);
-              o4.z = Cvt<T>::pack2(w[4], w[5]);
-              o4.w = Cvt<T>::pack2(w[6], w[7]);
-              *reinterpret_cast<uint4*>(my_stg + j * 2) = o4;
             }
           }
         }
         __syncwarp();
-        // ---- output: smem -> coalesced global stores ----
-        if (chunk_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (cunit < ounits && cok[i] && ocol0 + cunit * 8 < n_out) {
-              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + (i * 8 + (lane >> 2)) * kStgStride + cunit * 16);
-              *reinterpret_cast<uint4*>(C + crow[i] * p.ldc + ocol0 + cunit * 8) = v4;
-            }
-          }
-        }
-        if (c + 1 < BN / 32) tmem_ld_wait();
+        if (c + 1 < kChunks) tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();

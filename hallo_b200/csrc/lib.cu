@@ -6,6 +6,7 @@
 #include "attn2_tc.cu"
 #include "attn_api.cu"
 #include "aux.cu"
+#include "ubench.cu"
 
 extern "C" int hallo_b200_device_error(unsigned int* code_out) {
   unsigned int v = 0;

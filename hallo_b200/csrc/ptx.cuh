@@ -292,6 +292,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
+// erf-GELU with the Abramowitz-Stegun 7.1.26 erf (|abs err| < 1.5e-7): one rcp + one ex2 instead of erff()
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = poly * fast_exp2(-z * z * 1.4426950408889634f);   // 1 - erf(z)
+  const float erf_abs = 1.0f - e;
+  const float erfx = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfx);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 }  // namespace hb

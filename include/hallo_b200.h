@@ -200,6 +200,9 @@ int hallo_b200_advance_step(int32_t* step, int n_steps, hb_stream_t stream);
 int hallo_b200_tokens_to_bcfhw(int dtype, const void* x, int64_t ld, float* out, int B, int C, int F, int HW,
                                hb_stream_t stream);
 
+/* Instruction-throughput micro-benchmark (design evidence only; tools/ubench.py). Returns the thread count. */
+int hallo_b200_ubench_exp(int mode, int iters, float* scratch, hb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
