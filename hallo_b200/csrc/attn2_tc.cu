@@ -3,7 +3,8 @@
 //
 //   warp 0      TMA producer (Q_A, Q_B once; K_j / V_j through a 2-deep ring, shared by both tiles)
 //   warp 1      MMA issuer:  S_t = Q_t K_j^T (SS)  and  O_t += P_t V_j (TS: A operand = P in TMEM)
-//   warps 2-5   softmax of tile A   |  warps 6-9  softmax of tile B   (one thread per query row)
+//   warp 2      TMEM allocation;  warp 3 idle  (warpgroup 0 gives its registers away: setmaxnreg.dec 40)
+//   warps 4-7   softmax of tile A   |  warps 8-11  softmax of tile B   (one thread per query row, 232 regs)
 //
 // Issue order on the tensor pipe is  ... PV_A(j) QK_A(j+1) | PV_B(j) QK_B(j+1) ...  so while one tile's
 // softmax runs on the SFU / FMA pipes the other tile's MMAs run; tcgen05 ops of one thread execute in order,
@@ -14,7 +15,7 @@
 
 namespace hb {
 
-constexpr int kAttn2Threads = 320;
+constexpr int kAttn2Threads = 384;   // warpgroup 0: TMA / MMA / TMEM-alloc / idle; warpgroups 1, 2: softmax of tile A, B
 
 template <int D, int BN>
 struct Attn2Cfg {
@@ -91,6 +92,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
@@ -194,9 +197,11 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (++kstage == STAGES) { kstage = 0; kphase ^= 1; }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     // ============================ softmax warps ============================
-    const int t = (warp - 2) >> 2;                       // query tile of this warpgroup
+    const int t = (warp - 4) >> 2;                       // query tile of this warpgroup
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
@@ -217,8 +222,13 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool tail = (key0 + BN > p.L);
       float mx = -INFINITY;
       if (!tail) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains, 3-input max
 #pragma unroll
-        for (int i = 0; i < BN; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int i = 0; i < BN; i += 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m4[q] = max3(m4[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
 #pragma unroll
         for (int i = 0; i < BN; ++i)
@@ -244,7 +254,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         m_ref = m_new;
       }
-      float psum = 0.f;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
         float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref));
@@ -253,10 +263,10 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (key0 + i >= p.L) e0 = 0.f;
           if (key0 + i + 1 >= p.L) e1 = 0.f;
         }
-        psum += e0 + e1;
+        ps4[(i >> 1) & 3] += e0 + e1;
         s[i >> 1] = Cvt<T>::pack2(e0, e1);       // P packed two keys per 32-bit TMEM column
       }
-      l_sum += psum;
+      l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
 #pragma unroll
       for (int c = 0; c < BN / 64; ++c) tmem_st_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
       tmem_st_wait();

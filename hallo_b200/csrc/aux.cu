@@ -357,6 +357,91 @@ __global__ void __launch_bounds__(288) tattn_kernel(const T* __restrict__ Q, lon
   }
 }
 
+// Shared-memory variant: a CTA stages the K / V rows of PIX pixels (all Fk frames, all heads) with coalesced
+// 128-bit loads, then one thread per (pixel, head, query frame) runs the Fk-key softmax out of shared memory
+// (the lanes of a warp differ only in head / frame, so the 16-byte smem reads are conflict-free broadcasts).
+template <typename T, int MAXF>
+__global__ void __launch_bounds__(576) tattn_smem_kernel(const T* __restrict__ Q, long long ldq,
+                                                         const T* __restrict__ K,
+                                                         const T* __restrict__ V, long long ldkv,
+                                                         T* __restrict__ O, long long ldo, int Fq, int Fk,
+                                                         int L, int heads, int d, int pix_per_cta,
+                                                         float scale_log2) {
+  extern __shared__ uint4 sm4[];
+  const int C = heads * d;
+  const int cvec = C >> 3;                       // 16-byte vectors per row
+  const int b = blockIdx.y;
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int npix = min(pix_per_cta, L - pix0);
+  uint4* sK = sm4;                               // [Fk][pix_per_cta][cvec]
+  uint4* sV = sm4 + (size_t)Fk * pix_per_cta * cvec;
+  const int rows = Fk * npix;
+  for (int i = threadIdx.x; i < rows * cvec; i += blockDim.x) {
+    const int v = i % cvec;
+    const int r = i / cvec;
+    const int f = r / npix, p = r - f * npix;
+    const long long grow = ((long long)b * Fk + f) * L + pix0 + p;
+    sK[((size_t)f * pix_per_cta + p) * cvec + v] = *reinterpret_cast<const uint4*>(K + grow * ldkv + v * 8);
+    sV[((size_t)f * pix_per_cta + p) * cvec + v] = *reinterpret_cast<const uint4*>(V + grow * ldkv + v * 8);
+  }
+  __syncthreads();
+  const int per_pix = heads * Fq;
+  const int p = threadIdx.x / per_pix;
+  if (p >= npix) return;
+  const int rem = threadIdx.x - p * per_pix;
+  const int fq = rem / heads;
+  const int head = rem - fq * heads;
+  const int dvec = d >> 3;
+  const T* q = Q + (((long long)b * Fq + fq) * L + pix0 + p) * ldq + head * d;
+  float s[MAXF];
+#pragma unroll
+  for (int k = 0; k < MAXF; ++k) s[k] = 0.f;
+  for (int c = 0; c < dvec; ++c) {
+    float qv[8];
+    load8(q + c * 8, qv);
+#pragma unroll
+    for (int k = 0; k < MAXF; ++k) {
+      if (k < Fk) {
+        const uint4 u = sK[((size_t)k * pix_per_cta + p) * cvec + head * dvec + c];
+        const float2 a0 = Cvt<T>::unpack2(u.x), a1 = Cvt<T>::unpack2(u.y), a2 = Cvt<T>::unpack2(u.z),
+                     a3 = Cvt<T>::unpack2(u.w);
+        s[k] += qv[0] * a0.x + qv[1] * a0.y + qv[2] * a1.x + qv[3] * a1.y + qv[4] * a2.x + qv[5] * a2.y +
+                qv[6] * a3.x + qv[7] * a3.y;
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAXF; ++k)
+    if (k < Fk) mx = fmaxf(mx, s[k]);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXF; ++k) {
+    s[k] = (k < Fk) ? fast_exp2((s[k] - mx) * scale_log2) : 0.f;
+    sum += s[k];
+  }
+  const float inv = 1.f / sum;
+  T* o = O + (((long long)b * Fq + fq) * L + pix0 + p) * ldo + head * d;
+  for (int c = 0; c < dvec; ++c) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXF; ++k) {
+      if (k < Fk) {
+        const uint4 u = sV[((size_t)k * pix_per_cta + p) * cvec + head * dvec + c];
+        const float2 a0 = Cvt<T>::unpack2(u.x), a1 = Cvt<T>::unpack2(u.y), a2 = Cvt<T>::unpack2(u.z),
+                     a3 = Cvt<T>::unpack2(u.w);
+        acc[0] += s[k] * a0.x; acc[1] += s[k] * a0.y; acc[2] += s[k] * a1.x; acc[3] += s[k] * a1.y;
+        acc[4] += s[k] * a2.x; acc[5] += s[k] * a2.y; acc[6] += s[k] * a3.x; acc[7] += s[k] * a3.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    store8(o + c * 8, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------------
@@ -637,6 +722,27 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
   if (head_dim % 8 || Fk > 32 || Fk < 1 || ldq % 8 || ldkv % 8 || ldo % 8)
     return fail(HB_ERR_BAD_SHAPE, "temporal_attention: head_dim=%d Fk=%d", head_dim, Fk);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // shared-memory variant when one pixel's threads fit a CTA and its K/V rows fit shared memory
+    const int C = heads * head_dim;
+    const int per_pix = heads * Fq;
+    int ppc = 576 / per_pix;
+    const size_t row_bytes = (size_t)2 * Fk * C * 2;                 // K + V bytes of one pixel
+    while (ppc > 1 && ppc * row_bytes > 200 * 1024) --ppc;
+    if (ppc >= 1 && ppc * row_bytes <= 200 * 1024 && Fk <= 32 && C % 8 == 0) {
+      const size_t smem = ppc * row_bytes;
+      dim3 grid2((L + ppc - 1) / ppc, batch);
+      const float sc2 = (float)(1.4426950408889634 / sqrt((double)head_dim));
+      HB_DISPATCH_T(dtype, {
+        auto kern = Fk <= 18 ? tattn_smem_kernel<T, 18> : tattn_smem_kernel<T, 32>;
+        HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<grid2, ppc * per_pix, smem, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O, ldo, Fq,
+                                               Fk, L, heads, head_dim, ppc, sc2);
+      })
+      HB_LAUNCH_CHECK();
+      return HB_OK;
+    }
+  }
   const long long total = (long long)batch * Fq * L * heads;
   const int block = (heads * Fq <= 288 && (288 % (heads * Fq)) == 0) ? 288 : 256;   // whole pixels per CTA when possible
   const int grid = (int)((total + block - 1) / block);
