@@ -10,6 +10,15 @@
 //
 // Implicit conv: the A operand of tap (kh,kw) is the NHWC box shifted by (kh-1, kw-1); TMA's
 // out-of-bounds zero fill supplies the padding, so no im2col buffer exists anywhere.
+//
+// CG = 2 (CTA pair, tcgen05 cta_group::2): two CTAs of a cluster own a 256 x BN tile.  Each CTA stages its own
+// 128 A rows and HALF of the W rows, the leader issues one M=256 MMA per K step for both SMs and multicasts its
+// commits.  A single-CTA M=128 x N=160 MMA needs 9 KB of operand reads per 80 cycles on top of the TMA fill of the
+// same stage (~225 B/clk against a ~128 B/clk shared-memory port): measured 2x below the tensor-pipe rate
+// (profiles/r1_launches_v3_summary.txt).  Sharing W across the pair and widening BN to 192/256 brings the
+// shared-memory traffic back under the port limit.
+#include <cstdlib>
+
 #include "host_common.cuh"
 #include "ptx.cuh"
 
@@ -45,22 +54,27 @@ struct GemmDev {
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;   // a CTA of a pair stages half of the W rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
 
-template <typename T, int BN, int STAGES, bool CONV>
+template <typename T, int BN, int STAGES, bool CONV, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using SM = GemmSmem<BN, STAGES>;
+  using SM = GemmSmem<BN, STAGES, CG>;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cta_stride = gridDim.x / CG;          // persistent loop stride in units of (pairs of) CTAs
+  const int cta_first = blockIdx.x / CG;
   constexpr uint32_t kAccStride = 256;  // TMEM column offset between the two accumulator stages
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
+  static_assert(CG == 1 || CG == 2, "cta_group");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -81,22 +95,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);        // pair: leader's expect_tx arrive + the peer producer's remote arrive
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 8 * CG);  // pair: the epilogue warps of both CTAs release the leader's accumulator
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_cg2<512>(tmem_slot); else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // peer barriers must be initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // a pair walks (pairs of) M tiles: tile t covers M tiles {CG*tm2, CG*tm2 + 1}; this CTA takes tm = CG*tm2 + rank
+  const int num_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
   const int kblocks = p.K / kBK;
   const int cin_blocks = CONV ? p.cin / kBK : 1;
 
@@ -105,9 +123,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int tm = t / p.tiles_n;
-        const int tn = t - tm * p.tiles_n;
+      for (int t = cta_first; t < num_tiles; t += cta_stride) {
+        const int tm = (t / p.tiles_n) * CG + (int)rank;
+        const int tn = t % p.tiles_n;
         int n0 = 0, h0 = 0, w0 = 0;
         if (CONV) {
           int per_img = p.tiles_w * p.tiles_h;
@@ -123,7 +141,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x11);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           uint8_t* sb = sa + SM::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
+          if (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
+          }
           if (CONV) {
             int tap = kb / cin_blocks;
             int cb = kb - tap * cin_blocks;
@@ -132,19 +155,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // input is stored as 4 phase planes [(p*2+q)*img_n + n][h/2][w/2][C] (x[2i+p][2j+q]);
               // tap kh reads phase (kh==1 ? 0 : 1) at row offset (kh==0 ? -1 : 0)
               const int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
-              tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 - (kw == 0), h0 - (kh == 0),
-                          (ph * 2 + pw) * p.img_n + n0);
+              if (CG == 2) tma_load_4d_cg2(sa, &tmA, &full_bar[stage], cb * kBK, w0 - (kw == 0), h0 - (kh == 0),
+                                           (ph * 2 + pw) * p.img_n + n0);
+              else tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 - (kw == 0), h0 - (kh == 0),
+                               (ph * 2 + pw) * p.img_n + n0);
             } else {
-              tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
+              if (CG == 2) tma_load_4d_cg2(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
+              else tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBK, w0 + kw - 1, h0 + kh - 1, n0);
             }
           } else {
             int k = kb * kBK;
-            if (k < p.K1)
-              tma_load_2d(sa, &tmA, &full_bar[stage], k, tm * kBM);
-            else
-              tma_load_2d(sa, &tmA2, &full_bar[stage], k - p.K1, tm * kBM);
+            const CUtensorMap* ma = (k < p.K1) ? &tmA : &tmA2;
+            const int kk = (k < p.K1) ? k : k - p.K1;
+            if (CG == 2) tma_load_2d_cg2(sa, ma, &full_bar[stage], kk, tm * kBM);
+            else tma_load_2d(sa, ma, &full_bar[stage], kk, tm * kBM);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, tn * BN);
+          if (CG == 2) tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb * kBK, tn * BN + (int)rank * (BN / 2));
+          else tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, tn * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -154,11 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_f16(kBM, BN, Cvt<T>::kFmt, 0, 0);
+    constexpr uint32_t idesc = make_idesc_f16(kBM * CG, BN, Cvt<T>::kFmt, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    if (leader)   // in a pair only the leader CTA issues MMAs (for both SMs)
+    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1, 0x21);
@@ -175,10 +203,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 32 B (16 halfs) along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) umma_f16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+          if (CG == 2) {
+            umma_commit_cg2_mc(&empty_bar[stage]);
+            if (kb == kblocks - 1) umma_commit_cg2_mc(&tfull_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -198,9 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
     const int chalf = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int tm = t / p.tiles_n;
-      const int tn = t - tm * p.tiles_n;
+    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
+      const int tm = (t / p.tiles_n) * CG + (int)rank;
+      const int tn = t % p.tiles_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int r_in_tile = quarter * 32 + lane;
@@ -318,15 +352,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 2 && !leader) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // the peer may still be arriving on / reading this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (CG == 2) tmem_dealloc_cg2<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -348,9 +386,10 @@ static void pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
     }
 }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN, int STAGES, int CG>
 static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
-  using SM = GemmSmem<BN, STAGES>;
+  using SM = GemmSmem<BN, STAGES, CG>;
+  static_assert(SM::kTotal <= 232448, "gemm smem budget");
   GemmDev d{};
   d.M = q->M;
   d.N = q->N;
@@ -374,7 +413,7 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   {
     uint64_t dims[2] = {(uint64_t)q->K, (uint64_t)q->N};
     uint64_t str[1] = {(uint64_t)q->ldw * 2};
-    uint32_t box[2] = {kBK, (uint32_t)BN};
+    uint32_t box[2] = {kBK, (uint32_t)(BN / CG)};
     if ((rc = make_tmap_16b(&tmB, q->dtype, q->W, 2, dims, str, box)) != HB_OK) return rc;
   }
   if (q->conv3x3) {
@@ -418,18 +457,42 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
     }
   }
 
-  const int tiles = d.tiles_m * d.tiles_n;
+  const int tiles = ((d.tiles_m + CG - 1) / CG) * d.tiles_n;      // (pairs of) tiles
   if (tiles <= 0) return HB_OK;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true> : gemm_tc_kernel<T, BN, STAGES, false>;
+  const int max_ctas = num_sms() / CG;
+  const int grid = (tiles < max_ctas ? tiles : max_ctas) * CG;
+  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true, CG> : gemm_tc_kernel<T, BN, STAGES, false, CG>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[q->conv3x3 ? 1 : 0]) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set[q->conv3x3 ? 1 : 0] = true;
   }
-  kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(tmA, tmA2, tmB, d);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = SM::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, d));
   HB_LAUNCH_CHECK();
   return HB_OK;
+}
+
+template <typename T>
+static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
+  static const bool force1 = getenv("HALLO_B200_GEMM_1CTA") != nullptr;     // A/B switch for benchmarking
+  const int tiles_m = p->conv3x3 ? 2 : (p->M + kBM - 1) / kBM;
+  if (force1 || tiles_m < 2) return launch_gemm<T, 160, 5, 1>(p, s);
+  // widest N tile that divides N: fewer shared-memory bytes per MMA flop (see the header comment)
+  if (p->N % 256 == 0) return launch_gemm<T, 256, 6, 2>(p, s);
+  if (p->N % 192 == 0) return launch_gemm<T, 192, 7, 2>(p, s);
+  return launch_gemm<T, 160, 7, 2>(p, s);
 }
 
 }  // namespace hb
@@ -447,7 +510,7 @@ extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: bad K split %d of %d", p->K1, p->K);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // 160 divides every channel count of the UNet (320, 640, 1280, ...), so N tiles are never ragged.
-  if (p->dtype == HB_F16) return launch_gemm<__half, 160, 5>(p, s);
-  if (p->dtype == HB_BF16) return launch_gemm<__nv_bfloat16, 160, 5>(p, s);
+  if (p->dtype == HB_F16) return dispatch_gemm<__half>(p, s);
+  if (p->dtype == HB_BF16) return dispatch_gemm<__nv_bfloat16>(p, s);
   return fail(HB_ERR_BAD_DTYPE, "hallo_b200_gemm: dtype %d", p->dtype);
 }

@@ -19,7 +19,8 @@ TOL = {torch.float16: 2e-3, torch.bfloat16: 1.2e-2}
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 320, 320), (2048, 1280, 1280), (1000, 328, 192),
-                                   (8, 640, 768), (4096, 2560, 320)])
+                                   (8, 640, 768), (4096, 2560, 320), (512, 960, 320), (384, 1920, 640),
+                                   (300, 320, 64), (131072, 320, 320)])
 def test_gemm_plain(M, N, K, dtype):
     from hallo_b200 import ops
     dev = _dev()
