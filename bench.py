@@ -204,8 +204,17 @@ def main():
         eng.step()
         launches_per_step = lib.launch_count(reset=True)
     else:
-        eng.capture()
-        launches_per_step = lib.launch_count(reset=True) // 2      # capture() runs the step twice (warm-up + capture)
+        try:
+            eng.capture()
+            launches_per_step = lib.launch_count(reset=True) // 2  # capture() runs the step twice (warm-up + capture)
+        except Exception as e:                                     # e.g. a collective that refuses stream capture
+            print(f"# rank {rank}: CUDA-graph capture failed ({type(e).__name__}: {e}); stepping eagerly", file=sys.stderr)
+            eng.graph = None
+            torch.cuda.synchronize()
+            lib.launch_count(reset=True)
+            eng.step()
+            launches_per_step = lib.launch_count(reset=True)
+        config["cuda_graph"] = eng.graph is not None
     torch.cuda.synchronize()
 
     def barrier():

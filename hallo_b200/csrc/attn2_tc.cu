@@ -6,9 +6,10 @@
 //   warp 2      TMEM allocation;  warp 3 idle  (warpgroup 0 gives its registers away: setmaxnreg.dec 40)
 //   warps 4-7   softmax of tile A   |  warps 8-11  softmax of tile B   (one thread per query row, 232 regs)
 //
-// Issue order on the tensor pipe is  ... PV_A(j) QK_A(j+1) | PV_B(j) QK_B(j+1) ...  so while one tile's
-// softmax runs on the SFU / FMA pipes the other tile's MMAs run; tcgen05 ops of one thread execute in order,
-// which is what makes overwriting S_t (and the P_t aliased onto it) by QK_t(j+1) safe after PV_t(j).
+// S is double-buffered per tile (2 x BN columns): the tensor pipe runs  ... PV_A(j) QK_A(j+2) | PV_B(j) QK_B(j+2) ...
+// so S_t(j+1) is already waiting in TMEM when softmax_t(j) finishes -- no MMA latency on the softmax critical path
+// (the SFU is the bottleneck at head_dim 40).  tcgen05 ops of one thread execute in order, which
+// is what makes overwriting S_t[j&1] (and the P_t(j) aliased onto it) by QK_t(j+2) safe after PV_t(j).
 // Same operand layouts, segment (reference-KV concat) handling and lazy rescale as attn_tc.cu.
 #include "host_common.cuh"
 #include "ptx.cuh"
@@ -24,16 +25,18 @@ struct Attn2Cfg {
   static constexpr int kDv = ((D + 15) / 16) * 16;
   static constexpr int kQBytes = kChunks * 128 * 128;     // one Q tile
   static constexpr int kKVBytes = kChunks * BN * 128;
-  static constexpr int kStages = 2;
+  static constexpr int kKStages = 3;     // K_{j+2} is consumed while V_j is still in use
+  static constexpr int kVStages = 2;
   static constexpr int kOffK = 2 * kQBytes;
-  static constexpr int kOffV = kOffK + kStages * kKVBytes;
-  static constexpr int kOffBar = kOffV + kStages * kKVBytes;
+  static constexpr int kOffV = kOffK + kKStages * kKVBytes;
+  static constexpr int kOffBar = kOffV + kVStages * kKVBytes;
   static constexpr int kTotal = kOffBar + 256 + 1024;
-  static constexpr uint32_t kSCol0 = 0, kSCol1 = BN;          // S_A, S_B (P_t aliases the first BN/2 columns)
-  static constexpr uint32_t kOCol0 = 2 * BN;
-  static constexpr uint32_t kOCol1 = 2 * BN + ((kDv + 31) / 32) * 32;
+  // TMEM columns: S_t[b] at (2t + b) * BN (P_t(j) aliases the first BN/2 columns of S_t[j&1]); then O_A, O_B
+  static constexpr uint32_t kOCol0 = 4 * BN;
+  static constexpr uint32_t kOCol1 = 4 * BN + ((kDv + 31) / 32) * 32;
   static constexpr uint32_t kTmemCols = (kOCol1 + kDv) <= 256 ? 256 : 512;
   static_assert(kOCol1 + kDv <= 512, "TMEM budget");
+  static_assert(BN == 64, "P_t(j) = BN/2 = 32 columns, one tcgen05.st.x32");
 };
 
 template <typename T, int D, int BN>
@@ -42,20 +45,20 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                 const __grid_constant__ CUtensorMap tmV1, const AttnDev p) {
   using CF = Attn2Cfg<D, BN>;
-  constexpr int STAGES = CF::kStages;
+  constexpr int KST = CF::kKStages, VST = CF::kVStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF::kOffBar);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // STAGES
-  uint64_t* k_empty = k_full + STAGES;
-  uint64_t* v_full = k_empty + STAGES;
-  uint64_t* v_empty = v_full + STAGES;
-  uint64_t* s_full = v_empty + STAGES;     // 2 (tile A, tile B)
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* k_full = bars + 1;             // KST
+  uint64_t* k_empty = k_full + KST;
+  uint64_t* v_full = k_empty + KST;        // VST
+  uint64_t* v_empty = v_full + VST;
+  uint64_t* s_full = v_empty + VST;        // [tile][buffer] = 4
+  uint64_t* p_full = s_full + 4;           // 4
+  uint64_t* pv_done = p_full + 4;          // 2 (one completion per KV tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,17 +76,20 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < VST; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 4; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);
-      mbar_init(&o_done[t], 1);
     }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CF::kTmemCols>(tmem_slot);
@@ -104,30 +110,36 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < CF::kChunks; ++c)
           tma_load_4d(smem + t * CF::kQBytes + c * (128 * 128), &tmQ, q_full, c * 64, head,
                       qt * 256 + t * 128, frame);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < ntiles; ++j) {
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      auto load_k = [&](int j) {
         const int seg = j / tiles_per_seg;
         const int kt = j - seg * tiles_per_seg;
-        const CUtensorMap* mk = seg == 0 ? &tmK0 : &tmK1;
-        const CUtensorMap* mv = seg == 0 ? &tmV0 : &tmV1;
-        const int fr = seg == 0 ? frame : ref;
-        mbar_wait(&k_empty[stage], phase ^ 1, 0x71);
-        mbar_arrive_expect_tx(&k_full[stage], CF::kKVBytes);
+        mbar_wait(&k_empty[ks], kph ^ 1, 0x71);
+        mbar_arrive_expect_tx(&k_full[ks], CF::kKVBytes);
 #pragma unroll
         for (int c = 0; c < CF::kChunks; ++c)
-          tma_load_4d(smem + CF::kOffK + stage * CF::kKVBytes + c * (BN * 128), mk, &k_full[stage],
-                      c * 64, head, kt * BN, fr);
-        mbar_wait(&v_empty[stage], phase ^ 1, 0x72);
-        mbar_arrive_expect_tx(&v_full[stage], CF::kKVBytes);
+          tma_load_4d(smem + CF::kOffK + ks * CF::kKVBytes + c * (BN * 128), seg == 0 ? &tmK0 : &tmK1, &k_full[ks],
+                      c * 64, head, kt * BN, seg == 0 ? frame : ref);
+        if (++ks == KST) { ks = 0; kph ^= 1; }
+      };
+      auto load_v = [&](int j) {
+        const int seg = j / tiles_per_seg;
+        const int kt = j - seg * tiles_per_seg;
+        mbar_wait(&v_empty[vs], vph ^ 1, 0x72);
+        mbar_arrive_expect_tx(&v_full[vs], CF::kKVBytes);
 #pragma unroll
         for (int c = 0; c < CF::kChunks; ++c)
-          tma_load_4d(smem + CF::kOffV + stage * CF::kKVBytes + c * (BN * 128), mv, &v_full[stage],
-                      c * 64, head, kt * BN, fr);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+          tma_load_4d(smem + CF::kOffV + vs * CF::kKVBytes + c * (BN * 128), seg == 0 ? &tmV0 : &tmV1, &v_full[vs],
+                      c * 64, head, kt * BN, seg == 0 ? frame : ref);
+        if (++vs == VST) { vs = 0; vph ^= 1; }
+      };
+      // same order as the MMA warp consumes: K0 K1 | V0 K2 | V1 K3 | ...
+      load_k(0);
+      if (ntiles > 1) load_k(1);
+      for (int j = 0; j < ntiles; ++j) {
+        load_v(j);
+        if (j + 2 < ntiles) load_k(j + 2);
       }
     }
   } else if (warp == 1) {
@@ -137,64 +149,69 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK = smem_u32(smem + CF::kOffK);
     const uint32_t sV = smem_u32(smem + CF::kOffV);
-    const uint32_t s_col[2] = {tmem_base + CF::kSCol0, tmem_base + CF::kSCol1};
     const uint32_t o_col[2] = {tmem_base + CF::kOCol0, tmem_base + CF::kOCol1};
 
-    auto issue_qk = [&](int t, int stage) {
+    auto issue_qk = [&](int t, int buf, int stage) {
       const uint32_t qbase = sQ + t * CF::kQBytes;
       const uint32_t kbase = sK + stage * CF::kKVBytes;
+      const uint32_t scol = tmem_base + (2 * t + buf) * BN;
 #pragma unroll
       for (int k = 0; k < CF::kKSteps; ++k) {
         const uint32_t off_q = (k >> 2) * (128 * 128) + (k & 3) * 32;
         const uint32_t off_k = (k >> 2) * (BN * 128) + (k & 3) * 32;
-        umma_f16_ss(s_col[t], make_desc_sw128(qbase + off_q, 16, 1024),
-                    make_desc_sw128(kbase + off_k, 16, 1024), idesc_qk, k != 0);
+        umma_f16_ss(scol, make_desc_sw128(qbase + off_q, 16, 1024), make_desc_sw128(kbase + off_k, 16, 1024),
+                    idesc_qk, k != 0);
       }
     };
 
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
     mbar_wait(q_full, 0, 0x81);
-    mbar_wait(&k_full[0], 0, 0x82);
-    tc_fence_after();
-    if (lane == 0) {
-      issue_qk(0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
+    for (int j0 = 0; j0 < 2 && j0 < ntiles; ++j0) {       // prologue: S_t(0), S_t(1)
+      mbar_wait(&k_full[ks], kph, 0x82);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_qk(0, j0, ks);
+        umma_commit(&s_full[0 * 2 + j0]);
+        issue_qk(1, j0, ks);
+        umma_commit(&s_full[1 * 2 + j0]);
+        umma_commit(&k_empty[ks]);
+      }
+      __syncwarp();
+      if (++ks == KST) { ks = 0; kph ^= 1; }
     }
-    __syncwarp();
-    int kstage = 1 % STAGES, vstage = 0;
-    uint32_t kphase = (STAGES == 1) ? 1 : 0, vphase = 0;
 
     for (int j = 0; j < ntiles; ++j) {
-      const bool more = (j + 1 < ntiles);
+      const int buf = j & 1;
+      const bool more = (j + 2 < ntiles);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_full[t], j & 1, 0x83);
-        if (t == 0) mbar_wait(&v_full[vstage], vphase, 0x84);
-        if (more && t == 0) mbar_wait(&k_full[kstage], kphase, 0x85);
+        mbar_wait(&p_full[t * 2 + buf], (j >> 1) & 1, 0x83);
+        if (t == 0) mbar_wait(&v_full[vs], vph, 0x84);
+        if (more && t == 0) mbar_wait(&k_full[ks], kph, 0x85);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t vbase = sV + vstage * CF::kKVBytes;
+          const uint32_t vbase = sV + vs * CF::kKVBytes;
+          const uint32_t pcol = tmem_base + (2 * t + buf) * BN;
 #pragma unroll
           for (int k = 0; k < BN / 16; ++k) {
-            // A = P_t in TMEM: 16 keys = 8 packed 32-bit columns per K step
-            umma_f16_ts(o_col[t], s_col[t] + k * 8, make_desc_sw128(vbase + k * 2048, BN * 128, 1024),
-                        idesc_pv, (j | k) != 0);
+            // A = P_t(j) in TMEM: 16 keys = 8 packed 32-bit columns per K step
+            umma_f16_ts(o_col[t], pcol + k * 8, make_desc_sw128(vbase + k * 2048, BN * 128, 1024), idesc_pv,
+                        (j | k) != 0);
           }
-          if (t == 1) umma_commit(&v_empty[vstage]);
-          if (!more) umma_commit(&o_done[t]);
+          umma_commit(&pv_done[t]);
+          if (t == 1) umma_commit(&v_empty[vs]);
           if (more) {
-            issue_qk(t, kstage);
-            umma_commit(&s_full[t]);
-            if (t == 1) umma_commit(&k_empty[kstage]);
+            issue_qk(t, buf, ks);                        // S_t(j+2) overwrites S_t(j) / P_t(j): in order after PV_t(j)
+            umma_commit(&s_full[t * 2 + buf]);
+            if (t == 1) umma_commit(&k_empty[ks]);
           }
         }
         __syncwarp();
       }
-      if (++vstage == STAGES) { vstage = 0; vphase ^= 1; }
+      if (++vs == VST) { vs = 0; vph ^= 1; }
       if (more) {
-        if (++kstage == STAGES) { kstage = 0; kphase ^= 1; }
+        if (++ks == KST) { ks = 0; kph ^= 1; }
       }
     }
   }
@@ -205,7 +222,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
-    const uint32_t s_addr = tmem_base + lane_addr + (t == 0 ? CF::kSCol0 : CF::kSCol1);
+    const uint32_t s_base = tmem_base + lane_addr + (2 * t) * BN;
     const uint32_t o_addr = tmem_base + lane_addr + (t == 0 ? CF::kOCol0 : CF::kOCol1);
     float m_ref = -INFINITY;
     float l_sum = 0.f;
@@ -213,7 +230,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < ntiles; ++j) {
       const int kt = j % tiles_per_seg;
       const int key0 = kt * BN;
-      mbar_wait(&s_full[t], j & 1, 0x91);
+      const int buf = j & 1;
+      const uint32_t s_addr = s_base + buf * BN;
+      mbar_wait(&s_full[t * 2 + buf], (j >> 1) & 1, 0x91);
       tc_fence_after();
       uint32_t s[BN];
 #pragma unroll
@@ -239,7 +258,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_ref, mx);
         if (j > 0) {
-          // s_full(j) was committed after P_t V_{j-1}: O_t is quiescent here (in-order tensor pipe)
+          // O_t may only be touched once P_t(j-1) V_{j-1} has completed
+          mbar_wait(&pv_done[t], (j - 1) & 1, 0x93);
+          tc_fence_after();
           const float f = fast_exp2(m_ref - m_new);
 #pragma unroll
           for (int c = 0; c < CF::kDv / 8; ++c) {
@@ -267,16 +288,18 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         s[i >> 1] = Cvt<T>::pack2(e0, e1);       // P packed two keys per 32-bit TMEM column
       }
       l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-#pragma unroll
-      for (int c = 0; c < BN / 64; ++c) tmem_st_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_st_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
     }
 
     // ---- epilogue: O / l -> global ----
-    mbar_wait(&o_done[t], 0, 0x92);
+    // pv_done completes once per KV tile; only PV(ntiles-3) is known complete here, so walk the last two phases in
+    // order (a parity wait can only distinguish neighbouring phases)
+    if (ntiles >= 2) mbar_wait(&pv_done[t], (ntiles - 2) & 1, 0x94);
+    mbar_wait(&pv_done[t], (ntiles - 1) & 1, 0x92);
     tc_fence_after();
     const float inv = 1.0f / l_sum;
     const int qrow = qt * 256 + t * 128 + row;

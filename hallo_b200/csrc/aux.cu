@@ -126,7 +126,20 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x1,
     const T* base = first ? x1 + (long long)n * HW * C1 + cv * 8
                           : x2 + (long long)n * HW * C2 + (cv * 8 - C1);
     const int ld = first ? C1 : C2;
-    for (int p = p0 + py; p < p1; p += PY) {
+    int p = p0 + py;
+    for (; p + 3 * PY < p1; p += 4 * PY) {          // 4 independent 16-byte loads in flight per thread
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(base + (long long)(p + u * PY) * ld, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[u][j];
+          q[j] += v[u][j] * v[u][j];
+        }
+    }
+    for (; p < p1; p += PY) {
       float v[8];
       load8(base + (long long)p * ld, v);
 #pragma unroll
@@ -156,13 +169,29 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x1,
   }
 }
 
+// per-(frame, channel) scale / shift from the group sums:  y = x * sc + sh
+template <typename T>
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, const T* __restrict__ gamma,
+                                   const T* __restrict__ beta, float eps, int C, int G, int HW,
+                                   float* __restrict__ scsh) {
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int grp = c / cpg;
+    const float cnt = (float)cpg * HW;
+    const float m = stats[((long long)n * G + grp) * 2] / cnt;
+    const float var = fmaxf(stats[((long long)n * G + grp) * 2 + 1] / cnt - m * m, 0.f);
+    const float r = rsqrtf(var + eps);
+    const float g = Cvt<T>::to_f(gamma[c]);
+    scsh[((long long)n * 2) * C + c] = r * g;
+    scsh[((long long)n * 2 + 1) * C + c] = Cvt<T>::to_f(beta[c]) - m * r * g;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1, int C1,
                                                        const T* __restrict__ x2, int C2, int HW,
-                                                       int pix_per_cta, int G,
-                                                       const float* __restrict__ stats,
-                                                       const T* __restrict__ gamma,
-                                                       const T* __restrict__ beta, float eps,
+                                                       int pix_per_cta, const float* __restrict__ scsh,
                                                        int silu, T* __restrict__ out, int fpb_in,
                                                        int fpb_out, int frame_off) {
   // thread (cv, py): fixed 8 channels, strided pixels -> per-channel scale/shift live in registers
@@ -173,23 +202,14 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1,
   const int py = threadIdx.x / nvec;
   if (py >= PY) return;
   const int n = blockIdx.y;
-  const int cpg = C / G;
   const int c0 = cv * 8;
   float sc[8], sh[8];
   {
-    float g[8], b[8];
-    load8(gamma + c0, g);
-    load8(beta + c0, b);
-    const float cnt = (float)cpg * HW;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int grp = (c0 + j) / cpg;
-      const float m = stats[((long long)n * G + grp) * 2] / cnt;
-      const float var = fmaxf(stats[((long long)n * G + grp) * 2 + 1] / cnt - m * m, 0.f);
-      const float r = rsqrtf(var + eps);
-      sc[j] = r * g[j];
-      sh[j] = b[j] - m * r * g[j];
-    }
+    const float4* a = reinterpret_cast<const float4*>(scsh + ((long long)n * 2) * C + c0);
+    const float4* b = reinterpret_cast<const float4*>(scsh + ((long long)n * 2 + 1) * C + c0);
+    const float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
   }
   const int n_out = (n / fpb_in) * fpb_out + frame_off + (n % fpb_in);
   const bool first = c0 < C1;
@@ -661,12 +681,13 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
     return fail(HB_ERR_BAD_SHAPE, "groupnorm: C1=%d C2=%d G=%d", C1, C2, G);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   HB_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * G, s));
+  float* scsh = stats_ws + 2 * (size_t)N * G;          // workspace tail: [N][2][C] scale / shift
   const int nvec = C / 8;
   if (nvec > 512) return fail(HB_ERR_BAD_SHAPE, "groupnorm: C=%d too wide", C);
   int PY = 256 / nvec;
   if (PY < 1) PY = 1;
   const int threads = nvec * PY;
-  int pix_per_cta = 256;
+  int pix_per_cta = 64;                              // >= 2048 CTAs at 64x64x32 frames: enough loads in flight
   if (HW < pix_per_cta) pix_per_cta = HW;
   dim3 g1((HW + pix_per_cta - 1) / pix_per_cta, N);
   const size_t smem = sizeof(float) * 2 * PY * C;
@@ -675,12 +696,13 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
     gn_stats_kernel<T><<<g1, threads, smem, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, pix_per_cta, G,
                                                  stats_ws);
     HB_LAUNCH_CHECK();
+    gn_finalize_kernel<T><<<N, 256, 0, s>>>(stats_ws, (const T*)gamma, (const T*)beta, eps, C, G, HW, scsh);
+    HB_LAUNCH_CHECK();
     int ppc = 64;                                     // pixels per CTA of the apply pass
     if (HW < ppc) ppc = HW;
     dim3 g2((HW + ppc - 1) / ppc, N);
-    gn_apply_kernel<T><<<g2, threads, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, ppc, G, stats_ws,
-                                              (const T*)gamma, (const T*)beta, eps, silu, (T*)out, fpb_in,
-                                              fpb_out, frame_off);
+    gn_apply_kernel<T><<<g2, threads, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, ppc, scsh, silu, (T*)out,
+                                              fpb_in, fpb_out, frame_off);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;
@@ -728,7 +750,8 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
     const int per_pix = heads * Fq;
     int ppc = 576 / per_pix;
     const size_t row_bytes = (size_t)2 * Fk * C * 2;                 // K + V bytes of one pixel
-    while (ppc > 1 && ppc * row_bytes > 200 * 1024) --ppc;
+    while (ppc > 1 && ppc * row_bytes > 56 * 1024) --ppc;            // small CTAs: several resident per SM so the
+                                                                     // K/V fill of one overlaps the math of others
     if (ppc >= 1 && ppc * row_bytes <= 200 * 1024 && Fk <= 32 && C % 8 == 0) {
       const size_t smem = ppc * row_bytes;
       dim3 grid2((L + ppc - 1) / ppc, batch);

@@ -309,7 +309,7 @@ class DenoiseEngine:
                     tt = f"{l.motion}.temporal_transformer"
                     C = b.channels
                     gn18 = self.buf(f"{l.motion}.gn18", nb * (nm + fl) * L, C)
-                    ws = self.buf("gn_ws", 1, 2 * 64 * 64, torch.float32)
+                    ws = self.buf("gn_ws", 1, 2 * 64 * (64 + 2560), torch.float32)
                     ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
                                   n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
                                   fpb_in=nm, fpb_out=nm + fl, frame_off=0)
@@ -324,7 +324,7 @@ class DenoiseEngine:
 
     # ------------------------------------------------------------------ modules
     def _gn(self, x1, name, out, n_frames, hw, eps, silu, x2=None, **kw):
-        ws = self.buf("gn_ws", 1, 2 * 64 * 64, torch.float32)
+        ws = self.buf("gn_ws", 1, 2 * 64 * (64 + 2560), torch.float32)
         return ops.groupnorm(x1, self.W[f"{name}.w"], self.W[f"{name}.b"], out, ws, n_frames=n_frames, hw=hw,
                              groups=self.cfg.norm_num_groups, eps=eps, silu=silu, x2=x2, **kw)
 
@@ -618,7 +618,8 @@ class DenoiseEngine:
         self.latents.copy_(lat0)
         self.step_idx.copy_(st0)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures (multi-GPU shards)
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._forward()
             self._step_tail()
         self.graph = g

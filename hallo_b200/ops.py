@@ -165,9 +165,9 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: to
               x2: Optional[torch.Tensor] = None, fpb_in: int = 0, fpb_out: int = 0, frame_off: int = 0) -> torch.Tensor:
     """x1: [n_frames*hw, C1] contiguous, x2: optional [n_frames*hw, C2]; out: [*, C1+C2] contiguous."""
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous()) and out.is_contiguous()
-    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= 2 * n_frames * groups
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= 2 * n_frames * (groups + C1 + C2)
     lib.check(lib.load().hallo_b200_groupnorm(
         _i(lib.dtype_code(x1.dtype)), C.c_void_p(lib.ptr(x1)), _i(C1), C.c_void_p(lib.ptr(x2)), _i(C2), _i(n_frames),
         _i(hw), _i(groups), C.c_void_p(lib.ptr(gamma)), C.c_void_p(lib.ptr(beta)), C.c_float(eps), _i(1 if silu else 0),

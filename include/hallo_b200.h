@@ -157,7 +157,7 @@ int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void* out, int64
 /* Per-frame GroupNorm over channels-last frames [N, HW, C1(+C2)] (InflatedGroupNorm, resnet.py:88-101;
  * transformer_3d.py:197; motion_module.py:290), optional SiLU (resnet.py:386-387, 399).
  * x2/C2: second channel-concatenated source (UNet skip connection) or NULL/0.
- * stats_ws: fp32 [N*G*2] workspace.  Output frame n -> (n / fpb_in) * fpb_out + frame_off + n % fpb_in
+ * stats_ws: fp32 workspace of N*G*2 + N*2*(C1+C2) floats (group sums, then per-channel scale/shift).  Output frame n -> (n / fpb_in) * fpb_out + frame_off + n % fpb_in
  * (fpb_in <= 0: identity) -- used to drop frames into the 18-frame temporal buffer. */
 int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, int N, int HW, int G,
                          const void* gamma, const void* beta, float eps, int silu, void* out,

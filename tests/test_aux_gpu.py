@@ -69,7 +69,7 @@ def test_groupnorm(C1, C2, hw, silu):
     gam = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, DT)
     bet = (0.1 * torch.randn(C, generator=g)).to(dev, DT)
     out = torch.empty(n * hw, C, device=dev, dtype=DT)
-    ws = torch.empty(2 * n * 32, device=dev, dtype=torch.float32)
+    ws = torch.empty(2 * n * (32 + C), device=dev, dtype=torch.float32)
     ops.groupnorm(x1, gam, bet, out, ws, n_frames=n, hw=hw, eps=1e-5, silu=silu, x2=x2)
     torch.cuda.synchronize()
     xc = x1 if x2 is None else torch.cat([x1, x2], 1)
@@ -90,7 +90,7 @@ def test_groupnorm_frame_remap():
     gam = torch.ones(C, device=dev, dtype=DT)
     bet = torch.zeros(C, device=dev, dtype=DT)
     out = torch.zeros(b * (f + 2) * hw, C, device=dev, dtype=DT)
-    ws = torch.empty(2 * b * f * 32, device=dev, dtype=torch.float32)
+    ws = torch.empty(2 * b * f * (32 + C), device=dev, dtype=torch.float32)
     ops.groupnorm(x, gam, bet, out, ws, n_frames=b * f, hw=hw, eps=1e-6, fpb_in=f, fpb_out=f + 2, frame_off=2)
     torch.cuda.synchronize()
     ref = F.group_norm(x.float().view(b * f, hw, C).permute(0, 2, 1), 32, None, None, 1e-6).permute(0, 2, 1)
