@@ -348,6 +348,13 @@ struct Cvt<__nv_bfloat16> {
   }
 };
 
+// named barriers (ids 1..15; 0 is __syncthreads): sub-CTA producer/consumer hand-offs
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -356,6 +363,12 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile variant: keeps its place in the instruction stream (used to batch MUFU issue)
+__device__ __forceinline__ float fast_exp2_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
