@@ -277,6 +277,7 @@ def main():
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---------------- roofline of the dominant kernel (fused spatial + reference-KV attention, L0) ----------------
@@ -322,9 +323,18 @@ def main():
             agg.setdefault(kind, [0.0, 0])
             agg[kind][0] += a.elapsed_time(b_)
             agg[kind][1] += 1
+        prof_saved = ops.PROFILE
         ops.PROFILE = None
         eng.graph = eng.graph_saved
+        byname = {}
+        for name, a, b_ in prof_saved:
+            byname.setdefault(name, [0.0, 0])
+            byname[name][0] += a.elapsed_time(b_)
+            byname[name][1] += 1
         tot = sum(v[0] for v in agg.values())
+        print("# top shapes (eager, includes ~10 us launch gap each):", file=sys.stderr)
+        for k, v in sorted(byname.items(), key=lambda kv: -kv[1][0])[:28]:
+            print(f"#     {k:44s} {v[0]:8.3f} ms x{v[1]:3d}  {1e3 * v[0] / v[1]:8.1f} us each", file=sys.stderr)
         print(f"# per-op breakdown of one eager step ({tot:.2f} ms summed)", file=sys.stderr)
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"#   {k:22s} {v[0]:9.3f} ms  {100 * v[0] / tot:5.1f} %  x{v[1]}", file=sys.stderr)
@@ -345,6 +355,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

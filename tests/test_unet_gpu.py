@@ -84,3 +84,31 @@ def test_strict_state_dict_and_api_surface(model):
     assert m.config.cross_attention_dim == 768 and m.in_channels == 4 and m.dtype == torch.float16
     m2_missing = m.load_state_dict({k: v for k, v in m.state_dict().items()}, strict=True)
     assert not m2_missing.missing_keys and not m2_missing.unexpected_keys
+
+
+def test_unet_forward_bf16(model):
+    """config-4 dtype: bf16 storage / tensor-core inputs.  The reference's own bf16-vs-fp32 distance is 9.6e-3
+    (SURVEY.md 8c), so the tolerance against the fp32 golden is 3e-2."""
+    from hallo_b200.spec import UNetConfig
+    from hallo_b200.synth import synth_inputs
+    m, sd = model
+    dev = _dev()
+    fx = torch.load(os.path.join(GOLD, "unet_fwd_h16_f3.pt"), weights_only=False)
+    c = fx["case"]
+    inp = synth_inputs(UNetConfig(), c["h"], c["h"], c["f"], seed=c["seed"], timestep=c["t"], motion_scale=c["ms"])
+    try:
+        m.to(dtype=torch.bfloat16)
+        dt = torch.bfloat16
+        m.set_banks({k: v.to(dev) for k, v in inp["banks"].items()})
+        out = m(inp["sample"].to(dev, dt), torch.tensor(inp["timestep"]),
+                encoder_hidden_states=inp["encoder_hidden_states"].to(dev, dt),
+                audio_embedding=inp["audio_embedding"].to(dev, dt), mask_cond_fea=inp["mask_cond_fea"].to(dev, dt),
+                full_mask=[t.to(dev, dt) for t in inp["full_mask"]], face_mask=[t.to(dev, dt) for t in inp["face_mask"]],
+                lip_mask=[t.to(dev, dt) for t in inp["lip_mask"]], motion_scale=inp["motion_scale"], return_dict=False)[0]
+        torch.cuda.synchronize()
+        err = rel_l2(out, fx["out"])
+        print(f"bf16: rel L2 vs reference fp32 = {err:.3e}")
+        assert err < 3e-2
+    finally:
+        m.load_state_dict(sd, strict=True)          # restore exact fp16 weights for the other tests
+        m.to(dtype=torch.float16)
