@@ -79,6 +79,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _hard_exit():
+    """Multi-rank runs leave through os._exit: destroy_process_group() blocks for minutes when CUDA graphs that
+    captured NCCL collectives are still alive (measured: profiles/r1_debug_gather_2gpu.log)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def plan_shard(rank: int, world: int, n_frames: int):
     from hallo_b200.dist import plan_shard as ps
     return ps(rank, world, n_frames)
@@ -277,7 +285,7 @@ def main():
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
-            dist.destroy_process_group()
+            _hard_exit()
         return
 
     # ---------------- roofline of the dominant kernel (fused spatial + reference-KV attention, L0) ----------------
@@ -304,9 +312,17 @@ def main():
     attn_ms = sum(ts) / len(ts)
     attn_flops = spatial_attention_flops(L0, C0, n_cond, Bl - n_cond)
     achieved = attn_flops / (attn_ms * 1e-3) / 1e12
-    roofline = {"kernel": "attn_tc_kernel<D=40> (spatial self-attention + in-kernel reference-KV concat, L0)",
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        ns = json.load(open(os.path.join(ROOT, "profiles", "r1_attn_ncu_summary.json")))
+        if world == 1 and args.size == 64 and args.frames == 16:
+            traffic, traffic_src = ns["traffic_bytes"], "profiles/r1_attn_ncu_summary.json (ncu --set full, same shape)"
+    except Exception:
+        pass
+    roofline = {"kernel": "attn2_tc_kernel<D=40> (spatial self-attention + in-kernel reference-KV concat, L0)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["burst"], "traffic": None, "peak_source": f"bf16 burst, {peaks['src']}",
+                "frac": achieved / peaks["burst"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"bf16 burst, {peaks['src']}",
                 "ms_per_launch": attn_ms, "algorithmic_flops_per_launch": attn_flops,
                 "whole_step": {"achieved": fl["total"] * world / world / (ms_step * 1e-3) / 1e12 / world,
                                "peak": peaks["sustained"], "frac": fl["total"] / (ms_step * 1e-3) / 1e12 / world / peaks["sustained"],
@@ -351,11 +367,11 @@ def main():
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        _hard_exit()
 
 
 if __name__ == "__main__":

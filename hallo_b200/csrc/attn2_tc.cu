@@ -45,7 +45,8 @@ struct Attn2Cfg {
   static_assert(kOCol1 + kDv <= 512, "TMEM budget");
 };
 
-template <typename T, int D, int BN>
+// POLY: every POLY-th exponential of a row goes to the FMA pipe (exp2_poly) instead of the SFU; 0 = all on the SFU
+template <typename T, int D, int BN, int POLY>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -266,8 +267,10 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
-        float e0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref));
-        float e1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref));
+        const float x0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
+        const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
+        float e0 = (POLY > 0 && (i % POLY) == POLY - 1) ? exp2_poly(x0) : fast_exp2(x0);
+        float e1 = (POLY > 0 && ((i + 1) % POLY) == POLY - 1) ? exp2_poly(x1) : fast_exp2(x1);
         if (tail) {
           if (key0 + i >= p.L) e0 = 0.f;
           if (key0 + i + 1 >= p.L) e1 = 0.f;
@@ -314,7 +317,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <typename T, int D, int BN>
+template <typename T, int D, int BN, int POLY>
 static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   using CF = Attn2Cfg<D, BN>;
   static_assert(CF::kTotal <= 232448, "attention v2 smem budget");
@@ -340,7 +343,7 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   d.O = q->O;
   d.ldo = q->ldo;
   d.scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  auto kern = attn2_tc_kernel<T, D, BN>;
+  auto kern = attn2_tc_kernel<T, D, BN, POLY>;
   static bool attr_set = false;
   if (!attr_set) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kTotal));

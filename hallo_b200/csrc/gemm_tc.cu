@@ -50,6 +50,10 @@ struct GemmDev {
   long long ldr;
   float alpha;
   int flags;
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps;
+  float* stats_out;
   // conv geometry
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
@@ -262,6 +266,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const T* gb_row = nullptr;
       if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
       const int n_out = geglu ? (p.N >> 1) : p.N;
+      // folded LayerNorm of the A rows: v = rstd * (acc - mu * colsum[n])
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr && row_ok) {
+        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * row);
+        ln_mu = st.x / (float)p.K;
+        const float var = fmaxf(st.y / (float)p.K - ln_mu * ln_mu, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+      }
+      float osum = 0.f, osq = 0.f;
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
@@ -280,6 +293,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.ln_stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (col0 + j < p.N) {
+                const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + col0 + j);
+                v[j + 0] = ln_rstd * (v[j + 0] - ln_mu * cs.x);
+                v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * cs.y);
+                v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * cs.z);
+                v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * cs.w);
+              }
+            }
+          }
           if (bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
@@ -343,12 +368,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 o4.z = Cvt<T>::pack2(w[4], w[5]);
                 o4.w = Cvt<T>::pack2(w[6], w[7]);
                 *reinterpret_cast<uint4*>(C + row * p.ldc + col0 + j) = o4;
+                if (p.stats_out != nullptr) {
+                  // statistics of the values as the next LayerNorm will read them (rounded to the storage type)
+                  const float2 q0 = Cvt<T>::unpack2(o4.x), q1 = Cvt<T>::unpack2(o4.y), q2 = Cvt<T>::unpack2(o4.z),
+                               q3 = Cvt<T>::unpack2(o4.w);
+                  osum += (q0.x + q0.y) + (q1.x + q1.y) + (q2.x + q2.y) + (q3.x + q3.y);
+                  osq += (q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y) + (q2.x * q2.x + q2.y * q2.y) +
+                         (q3.x * q3.x + q3.y * q3.y);
+                }
               }
             }
           }
         }
         __syncwarp();
         if (c + 1 < kChunks) tmem_ld_wait();
+      }
+      if (p.stats_out != nullptr && row_ok) {
+        atomicAdd(p.stats_out + 2 * row, osum);
+        atomicAdd(p.stats_out + 2 * row + 1, osq);
       }
       tc_fence_before();
       __syncwarp();
@@ -406,6 +443,10 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   d.ldr = q->ldr;
   d.alpha = q->alpha;
   d.flags = q->flags;
+  d.ln_stats = q->ln_stats;
+  d.ln_colsum = q->ln_colsum;
+  d.ln_eps = q->ln_eps;
+  d.stats_out = q->stats_out;
   d.tiles_n = (q->N + BN - 1) / BN;
 
   CUtensorMap tmA, tmA2, tmB;
@@ -506,6 +547,10 @@ extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
   if (p->N % 8 != 0 || p->lda % 8 != 0 || p->ldw % 8 != 0 || p->ldc % 8 != 0 ||
       (p->residual && p->ldr % 8 != 0) || ((p->flags & HB_EPI_GEGLU) && p->N % 16 != 0))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: leading dims / N must be multiples of 8");
+  if ((p->ln_stats != nullptr) != (p->ln_colsum != nullptr) || (p->ln_stats != nullptr && (p->conv3x3 || p->N % 4 != 0)))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: ln_stats and ln_colsum go together (plain GEMM only)");
+  if (p->stats_out != nullptr && (p->flags & HB_EPI_GEGLU))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: stats_out is not defined for the GEGLU epilogue");
   if (p->A2 != nullptr && (p->K1 % kBK != 0 || p->K1 <= 0 || p->K1 >= p->K || p->conv3x3))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: bad K split %d of %d", p->K1, p->K);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -75,10 +75,15 @@ class PackedWeights:
         def qkv(name, out_name):
             put(out_name, torch.cat([sd[f"{name}.to_q.weight"], sd[f"{name}.to_k.weight"], sd[f"{name}.to_v.weight"]], 0))
 
-        def ff(name):
+        def fold(out_name, w, b, norm_name):
+            """LayerNorm(norm_name) -> Linear(w, b) folded into the GEMM epilogue (ops.fold_layernorm)."""
+            wg, cs, bb = ops.fold_layernorm(w.to(device), None if b is None else b.to(device),
+                                            sd[f"{norm_name}.weight"].to(device), sd[f"{norm_name}.bias"].to(device), dtype)
+            self.t[f"{out_name}.lnw"], self.t[f"{out_name}.lncs"], self.t[f"{out_name}.lnb"] = wg, cs, bb
+
+        def ff(name, norm_name):
             wi, bi = ops.pack_geglu_weight(sd[f"{name}.net.0.proj.weight"], sd[f"{name}.net.0.proj.bias"])
-            put(f"{name}.w1", wi)
-            put(f"{name}.b1", bi)
+            fold(f"{name}.w1", wi, bi, norm_name)
             lin(f"{name}.net.2")
 
         # stem / head
@@ -127,22 +132,25 @@ class PackedWeights:
                     norm(f"{n}.norm"); lin(f"{n}.proj_in"); lin(f"{n}.proj_out")
                     for k in ("norm1", "norm2", "norm3"):
                         norm(f"{tb}.{k}")
-                    qkv(f"{tb}.attn1", f"{tb}.attn1.qkv")
+                    fold(f"{tb}.attn1.qkv", torch.cat([sd[f"{tb}.attn1.to_q.weight"], sd[f"{tb}.attn1.to_k.weight"],
+                                                       sd[f"{tb}.attn1.to_v.weight"]], 0), None, f"{tb}.norm1")
                     put(f"{tb}.attn1.kv", torch.cat([sd[f"{tb}.attn1.to_k.weight"], sd[f"{tb}.attn1.to_v.weight"]], 0))
                     lin(f"{tb}.attn1.to_out.0")
-                    put(f"{tb}.attn2.q", sd[f"{tb}.attn2.to_q.weight"])
+                    fold(f"{tb}.attn2.q", sd[f"{tb}.attn2.to_q.weight"], None, f"{tb}.norm2")
                     put(f"{tb}.attn2.kv", torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], 0))
                     lin(f"{tb}.attn2.to_out.0")
-                    ff(f"{tb}.ff")
+                    ff(f"{tb}.ff", f"{tb}.norm3")
                 if l.audio:
                     n = l.audio
                     tb = f"{n}.transformer_blocks.0"
                     norm(f"{n}.norm"); lin(f"{n}.proj_in"); lin(f"{n}.proj_out")
                     for k in ("norm1", "norm2", "norm3"):
                         norm(f"{tb}.{k}")
-                    qkv(f"{tb}.attn1", f"{tb}.attn1.qkv")
+                    fold(f"{tb}.attn1.qkv", torch.cat([sd[f"{tb}.attn1.to_q.weight"], sd[f"{tb}.attn1.to_k.weight"],
+                                                       sd[f"{tb}.attn1.to_v.weight"]], 0), None, f"{tb}.norm1")
                     lin(f"{tb}.attn1.to_out.0")
-                    put(f"{tb}.attn2.q3", torch.cat([sd[f"{tb}.attn2_{r}.to_q.weight"] for r in range(3)], 0))
+                    fold(f"{tb}.attn2.q3", torch.cat([sd[f"{tb}.attn2_{r}.to_q.weight"] for r in range(3)], 0), None,
+                         f"{tb}.norm2")
                     put(f"{tb}.attn2.kv6", torch.cat([torch.cat([sd[f"{tb}.attn2_{r}.to_k.weight"],
                                                                  sd[f"{tb}.attn2_{r}.to_v.weight"]], 0)
                                                       for r in range(3)], 0))
@@ -154,19 +162,20 @@ class PackedWeights:
                          for r in ("full", "face", "lip")], 0).to(device)
                     self.t[f"{tb}.zero.b"] = torch.stack([sd[f"{tb}.zero_conv_{r}.bias"].float()
                                                           for r in ("full", "face", "lip")], 0).to(device)
-                    ff(f"{tb}.ff")
+                    ff(f"{tb}.ff", f"{tb}.norm3")
                 if l.motion and l.motion_executed:
                     tt = f"{l.motion}.temporal_transformer"
                     tb = f"{tt}.transformer_blocks.0"
                     norm(f"{tt}.norm"); lin(f"{tt}.proj_in"); lin(f"{tt}.proj_out")
                     for a in range(2):
-                        norm(f"{tb}.norms.{a}")
-                        qkv(f"{tb}.attention_blocks.{a}", f"{tb}.attention_blocks.{a}.qkv")
-                        lin(f"{tb}.attention_blocks.{a}.to_out.0")
-                        self.t[f"{tb}.attention_blocks.{a}.pe"] = \
-                            sd[f"{tb}.attention_blocks.{a}.pos_encoder.pe"][0].float().to(device).contiguous()
-                    norm(f"{tb}.ff_norm")
-                    ff(f"{tb}.ff")
+                        ab = f"{tb}.attention_blocks.{a}"
+                        wqkv = torch.cat([sd[f"{ab}.to_q.weight"], sd[f"{ab}.to_k.weight"], sd[f"{ab}.to_v.weight"]], 0)
+                        fold(f"{ab}.qkv", wqkv, None, f"{tb}.norms.{a}")
+                        lin(f"{ab}.to_out.0")
+                        # (LN(x) + pe) W^T = LN(x) W^T + pe W^T: the positional term becomes a per-frame bias row
+                        pe = sd[f"{ab}.pos_encoder.pe"][0].float().to(device)
+                        self.t[f"{ab}.pew"] = (pe @ wqkv.float().to(device).t()).to(dtype).contiguous()
+                    ff(f"{tb}.ff", f"{tb}.ff_norm")
             if b.downsampler:
                 conv3(f"{b.downsampler}.conv")
             if b.upsampler:
@@ -209,6 +218,9 @@ class DenoiseEngine:
         self.guidance = 1.0
         self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
         self.model_out: Optional[torch.Tensor] = None
+        self._stats_arena: Optional[torch.Tensor] = None    # fp32 (sum, sumsq) rows feeding the folded LayerNorms
+        self._stats_views: Dict[str, torch.Tensor] = {}
+        self._stats_used = 0
         self.sample: Optional[torch.Tensor] = None      # per-half fp32 sample for the plain forward() API path
 
     # ------------------------------------------------------------------ buffers
@@ -230,6 +242,22 @@ class DenoiseEngine:
         if isinstance(cur, torch.Tensor):
             self.graph = None            # shapes changed: any captured graph is stale
         return self.window[key]
+
+    def _stats(self, key: str, rows: int) -> torch.Tensor:
+        """[rows, 2] fp32 slice of the statistics arena (one per LayerNorm site; the arena is zeroed once per step)."""
+        v = self._stats_views.get(key)
+        if v is None:
+            if self._stats_arena is None:
+                # upper bound: 9 LN sites per cross layer, rows <= nb * (nm + fl) * L0
+                nsite = 9 * sum(len(b.layers) for b in self.W.blocks if b.kind in ("down_x", "up_x", "mid"))
+                cap = 2 * nsite * self.nb * (self.nm + self.fl) * self.h * self.w
+                self._stats_arena = torch.zeros(cap, dtype=torch.float32, device=self.dev)
+            n = 2 * rows
+            assert self._stats_used + n <= self._stats_arena.numel()
+            v = self._stats_arena[self._stats_used:self._stats_used + n].view(rows, 2)
+            self._stats_used += n
+            self._stats_views[key] = v
+        return v
 
     def L(self, level: int) -> int:
         hh, ww = self.level_hw[level]
@@ -261,7 +289,8 @@ class DenoiseEngine:
         ridx = [(-1 if n < f else (n % 2)) for n in rows]
         self._wset("ref_index", torch.tensor(ridx, dtype=torch.int32, device=dev))
         # temporal positions: motion frames 0..nm-1, then nm + global frame id
-        self._wset("pe_index", torch.tensor(list(range(nm)) + [nm + g for g in frames], dtype=torch.int32, device=dev))
+        win["pe_index"] = self._wset("pe_index", torch.tensor(list(range(nm)) + [nm + g for g in frames],
+                                                              dtype=torch.int32, device=dev))
 
         ehs = encoder_hidden_states.to(dev, dt)[halves]                       # [nb, 4, 768]
         aud = audio_embedding.to(dev, dt)[halves][:, fr_idx]                  # [nb, fl, 32, 768]
@@ -305,6 +334,11 @@ class DenoiseEngine:
                     self._wset(f"{l.audio}.zero.w", torch.cat([ms[r] * zw[r] for r in range(3)], 1).to(dt).contiguous())
                     self._wset(f"{l.audio}.zero.b", sum(ms[r] * zb[r] for r in range(3)).to(dt).contiguous())
                 if l.motion and l.motion_executed:
+                    tbm = f"{l.motion}.temporal_transformer.transformer_blocks.0"
+                    for a in range(2):
+                        pew = W[f"{tbm}.attention_blocks.{a}.pew"]                 # [pe_max_len, 3C]
+                        rows_pe = pew[win["pe_index"].long()]                        # [nm + fl, 3C]
+                        self._wset(f"{l.motion}.pegb.{a}", rows_pe.repeat(nb, 1).contiguous())
                     # GroupNorm of the motion frames is step-invariant: normalise once into frames [0, nm)
                     tt = f"{l.motion}.temporal_transformer"
                     C = b.channels
@@ -356,12 +390,13 @@ class DenoiseEngine:
         ops.conv3x3(t3.view(B, hh, ww, cout), W[f"{rs.name}.conv2.w"], out, bias=W[f"{rs.name}.conv2.b"], residual=sc)
         return out
 
-    def _ff(self, x, name, norm_name, tag):
+    def _ff(self, x, x_stats, name, tag):
+        """x + FF(LN(x)); the LayerNorm is folded into the GEGLU GEMM (x_stats = row statistics of x)."""
         W = self.W
-        n = self._ln(x, norm_name, "ln")
         M, C = x.shape
         g = self.buf("ff.mid", M, 4 * C)
-        ops.gemm(n, W[f"{name}.w1"], g, bias=W[f"{name}.b1"], geglu=True)
+        ops.gemm(x, W[f"{name}.w1.lnw"], g, bias=W[f"{name}.w1.lnb"], geglu=True, ln_stats=x_stats,
+                 ln_colsum=W[f"{name}.w1.lncs"])
         out = self.buf(tag, M, C)
         ops.gemm(g, W[f"{name}.net.2.w"], out, bias=W[f"{name}.net.2.b"], residual=x)
         return out
@@ -374,26 +409,27 @@ class DenoiseEngine:
         t = self.buf("tf.gn", M, C)
         self._gn(x, f"{name}.norm", t, B, L, 1e-6, False)
         h = self.buf("tf.h0", M, C)
-        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"])
-        n1 = self._ln(h, f"{tb}.norm1", "ln")
+        st0, st1, st2 = (self._stats(f"{name}.st{i}", M) for i in range(3))
+        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"], stats_out=st0)
         qkv = self.buf("tf.qkv", M, 3 * C)
-        ops.gemm(n1, W[f"{tb}.attn1.qkv"], qkv)
+        ops.gemm(h, W[f"{tb}.attn1.qkv.lnw"], qkv, bias=W[f"{tb}.attn1.qkv.lnb"], ln_stats=st0,
+                 ln_colsum=W[f"{tb}.attn1.qkv.lncs"])                                   # LN1 folded
         a = self.buf("tf.attn", M, C)
         kvref = win[f"{name}.kvref"]
         ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], a, heads=H, L=L, kref=kvref[:, :C], vref=kvref[:, C:],
                       ref_index=win["ref_index"])
         h1 = self.buf("tf.h1", M, C)
-        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h)
-        n2 = self._ln(h1, f"{tb}.norm2", "ln")
+        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h, stats_out=st1)
         q2 = self.buf("tf.q2", M, C)
-        ops.gemm(n2, W[f"{tb}.attn2.q"], q2)
+        ops.gemm(h1, W[f"{tb}.attn2.q.lnw"], q2, bias=W[f"{tb}.attn2.q.lnb"], ln_stats=st1,
+                 ln_colsum=W[f"{tb}.attn2.q.lncs"])                                      # LN2 folded
         kvi = win[f"{name}.kvimg"]
         a2 = self.buf("tf.attn", M, C)
         ops.cross_attention(q2, kvi[:, :C], kvi[:, C:], a2, frames=B, tokens=L, heads=H, head_dim=C // H,
                             n_keys=win["n_img_tokens"], kv_frame_div=self.fl)
         h2 = self.buf("tf.h2", M, C)
-        ops.gemm(a2, W[f"{tb}.attn2.to_out.0.w"], h2, bias=W[f"{tb}.attn2.to_out.0.b"], residual=h1)
-        h3 = self._ff(h2, f"{tb}.ff", f"{tb}.norm3", "tf.h3")
+        ops.gemm(a2, W[f"{tb}.attn2.to_out.0.w"], h2, bias=W[f"{tb}.attn2.to_out.0.b"], residual=h1, stats_out=st2)
+        h3 = self._ff(h2, st2, f"{tb}.ff", "tf.h3")
         out = self.buf(out_tag, M, C)
         ops.gemm(h3, W[f"{name}.proj_out.w"], out, bias=W[f"{name}.proj_out.b"], residual=x)
         return out
@@ -406,17 +442,18 @@ class DenoiseEngine:
         t = self.buf("tf.gn", M, C)
         self._gn(x, f"{name}.norm", t, B, L, 1e-6, False)
         h = self.buf("au.h0", M, Ci)
-        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"])
-        n1 = self._ln(h, f"{tb}.norm1", "ln")
+        st0, st1, st2 = (self._stats(f"{name}.st{i}", M) for i in range(3))
+        ops.gemm(t, W[f"{name}.proj_in.w"], h, bias=W[f"{name}.proj_in.b"], stats_out=st0)
         qkv = self.buf("tf.qkv", M, 3 * Ci)
-        ops.gemm(n1, W[f"{tb}.attn1.qkv"], qkv)
+        ops.gemm(h, W[f"{tb}.attn1.qkv.lnw"], qkv, bias=W[f"{tb}.attn1.qkv.lnb"], ln_stats=st0,
+                 ln_colsum=W[f"{tb}.attn1.qkv.lncs"])
         a = self.buf("tf.attn", M, Ci)
         ops.attention(qkv[:, :Ci], qkv[:, Ci:2 * Ci], qkv[:, 2 * Ci:], a, heads=H, L=L)
         h1 = self.buf("au.h1", M, Ci)
-        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h)
-        n2 = self._ln(h1, f"{tb}.norm2", "ln")
+        ops.gemm(a, W[f"{tb}.attn1.to_out.0.w"], h1, bias=W[f"{tb}.attn1.to_out.0.b"], residual=h, stats_out=st1)
         q3 = self.buf("au.q3", M, 3 * Ci)
-        ops.gemm(n2, W[f"{tb}.attn2.q3"], q3)
+        ops.gemm(h1, W[f"{tb}.attn2.q3.lnw"], q3, bias=W[f"{tb}.attn2.q3.lnb"], ln_stats=st1,
+                 ln_colsum=W[f"{tb}.attn2.q3.lncs"])
         kva = win[f"{name}.kvaud"]
         a3 = self.buf("au.a3", M, 3 * Ci)
         ops.cross_attention(q3, kva[:, :Ci], kva[:, Ci:2 * Ci], a3, frames=B, tokens=L, heads=H, head_dim=Ci // H,
@@ -427,8 +464,8 @@ class DenoiseEngine:
             ops.gemm(a3[:, r * Ci:(r + 1) * Ci], W[f"{tb}.attn2_{r}.to_out.0.w"], m3[:, r * Ci:(r + 1) * Ci],
                      bias=W[f"{tb}.attn2_{r}.to_out.0.b"], row_scale=win[f"mask.{rn}.{depth}"])
         h2 = self.buf("au.h2", M, Ci)
-        ops.gemm(m3, win[f"{name}.zero.w"], h2, bias=win[f"{name}.zero.b"], residual=h1)
-        h3 = self._ff(h2, f"{tb}.ff", f"{tb}.norm3", "au.h3")
+        ops.gemm(m3, win[f"{name}.zero.w"], h2, bias=win[f"{name}.zero.b"], residual=h1, stats_out=st2)
+        h3 = self._ff(h2, st2, f"{tb}.ff", "au.h3")
         out = self.buf(out_tag, M, C)
         ops.gemm(h3, W[f"{name}.proj_out.w"], out, bias=W[f"{name}.proj_out.b"], residual=x)
         return out
@@ -462,20 +499,21 @@ class DenoiseEngine:
         gn18 = self.buf(f"{name}.gn18", Mm, C)          # frames [0, nm) were filled in begin_window
         self._gn(x, f"{tt}.norm", gn18, nb * fl, L, 1e-6, False, fpb_in=fl, fpb_out=Fl, frame_off=nm)
         h = self.buf("mm.h", Mm, C)
-        ops.gemm(gn18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"])
+        st = [self._stats(f"{name}.st{i}", Mm) for i in range(3)]
+        ops.gemm(gn18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"], stats_out=st[0])
         for a in range(2):
-            n = self._ln(h, f"{tb}.norms.{a}", "mm.ln", pe=W[f"{tb}.attention_blocks.{a}.pe"], pe_index=win["pe_index"],
-                         tokens_per_frame=L, frames=Fl)
+            ab = f"{tb}.attention_blocks.{a}"
             qkv = self.buf("mm.qkv", Mm, 3 * C)
-            ops.gemm(n, W[f"{tb}.attention_blocks.{a}.qkv"], qkv)
+            # LN folded; the sinusoidal PE that the reference adds after the norm is the per-frame bias row pe W^T
+            ops.gemm(h, W[f"{ab}.qkv.lnw"], qkv, bias=W[f"{ab}.qkv.lnb"], ln_stats=st[a], ln_colsum=W[f"{ab}.qkv.lncs"],
+                     group_bias=win[f"{name}.pegb.{a}"], rows_per_group=L)
             k, v, Fk = self._gather_kv(qkv, C, L)
             o = self.buf("mm.attn", Mm, C)
             ops.temporal_attention(qkv[:, :C], k, v, o, batch=nb, fq=Fl, fk=Fk, tokens=L, heads=H)
             h2 = self.buf(f"mm.h{a + 1}", Mm, C)
-            ops.gemm(o, W[f"{tb}.attention_blocks.{a}.to_out.0.w"], h2,
-                     bias=W[f"{tb}.attention_blocks.{a}.to_out.0.b"], residual=h)
+            ops.gemm(o, W[f"{ab}.to_out.0.w"], h2, bias=W[f"{ab}.to_out.0.b"], residual=h, stats_out=st[a + 1])
             h = h2
-        h = self._ff(h, f"{tb}.ff", f"{tb}.ff_norm", "mm.h3")
+        h = self._ff(h, st[2], f"{tb}.ff", "mm.h3")
         out = self.buf(out_tag, nb * fl * L, C)
         for b in range(nb):                              # proj_out only on the real frames (drops motion frames)
             rows_in = slice((b * Fl + nm) * L, (b + 1) * Fl * L)
@@ -498,6 +536,8 @@ class DenoiseEngine:
         h, w = self.h, self.w
         L0 = h * w
         c0 = cfg.block_out_channels[0]
+        if self._stats_used:
+            self._stats_arena[:self._stats_used].zero_()   # one memset for all folded-LayerNorm statistics of this step
         # time embedding (unet_3d.py:565-588) -> SiLU(emb) -> all 22 time_emb_proj at once
         emb = self.buf("temb.sin", self.nb, c0)
         ops.timestep_embed(self.t_table, self.step_idx, emb)

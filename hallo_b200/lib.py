@@ -33,6 +33,8 @@ class GemmParams(C.Structure):
         ("flags", C.c_int32),
         ("conv3x3", C.c_int32),
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
+        ("stats_out", C.c_void_p),
     ]
 
 

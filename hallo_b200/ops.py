@@ -44,7 +44,9 @@ def _rowmajor_ld(t: torch.Tensor) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          group_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0, alpha: float = 1.0,
-         geglu: bool = False, silu: bool = False, a2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         geglu: bool = False, silu: bool = False, a2: Optional[torch.Tensor] = None,
+         ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M, N(/2)] = epilogue(cat([a, a2], 1) @ w.T); see include/hallo_b200.h."""
     p = lib.GemmParams()
     p.dtype = lib.dtype_code(a.dtype)
@@ -68,6 +70,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         p.residual, p.ldr = lib.ptr(residual), _rowmajor_ld(residual)
     p.alpha = alpha
     p.flags = (lib.HB_EPI_GEGLU if geglu else 0) | (lib.HB_EPI_SILU if silu else 0)
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.numel() >= 2 * M and ln_colsum.dtype == torch.float32
+        assert ln_colsum.numel() == N and ln_stats.is_contiguous() and ln_colsum.is_contiguous()
+        p.ln_stats, p.ln_colsum, p.ln_eps = lib.ptr(ln_stats), lib.ptr(ln_colsum), ln_eps
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.numel() >= 2 * M and stats_out.is_contiguous()
+        p.stats_out = lib.ptr(stats_out)
     lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "gemm")
     return out
 
@@ -294,3 +303,15 @@ def tokens_to_bcfhw(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
                                                     C.c_int64(_rowmajor_ld(x)), C.c_void_p(lib.ptr(out)), _i(b), _i(c),
                                                     _i(f), _i(h * w), lib.current_stream()), "tokens_to_bcfhw")
     return out
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, dtype):
+    """nn.LayerNorm(gamma, beta) -> nn.Linear(w, b) folded for hallo_b200_gemm's ln_* epilogue.
+    Returns (W*diag(gamma) in `dtype`, fp32 row sums of that packed matrix, W beta + b in `dtype`)."""
+    wf = w.float()
+    wg = (wf * gamma.float()[None, :]).to(dtype)
+    colsum = wg.float().sum(dim=1).contiguous()
+    bb = wf @ beta.float()
+    if b is not None:
+        bb = bb + b.float()
+    return wg.contiguous(), colsum, bb.to(dtype).contiguous()

@@ -100,6 +100,16 @@ typedef struct {
   int32_t flags;
   int32_t conv3x3;
   int32_t img_n, img_h, img_w;
+  /* LayerNorm folded into the GEMM (nn.LayerNorm -> nn.Linear chains of attention.py / motion_module.py):
+   *   LN(x) W^T = rstd_r * (x (W diag(gamma))^T - mu_r * colsum_n) + (W beta + b)_n
+   * W must already hold W*diag(gamma), bias W*beta + b.  ln_stats: fp32 [M,2] = (sum, sum of squares) of each A row,
+   * accumulated by the producing GEMM through stats_out; ln_colsum: fp32 [N] row sums of the packed W.  NULL = off. */
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps;
+  /* fp32 [M,2]: atomically accumulates (sum, sum of squares) of every output row over the stored columns (zeroed by
+   * the caller) -- feeds the next folded LayerNorm.  NULL = off. */
+  float* stats_out;
 } hb_gemm_params;
 
 int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream);

@@ -99,3 +99,37 @@ def test_conv3x3(n, h, w, cin, cout):
     torch.cuda.synchronize()
     ref = F.conv2d(x.float(), wt.float(), b.float(), padding=1).permute(0, 2, 3, 1).reshape(n * h * w, cout)
     assert rel_l2(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(2048, 320, 960, False), (1024, 640, 5120, True), (777, 1280, 1280, False)])
+def test_layernorm_folded_into_gemm(M, C, N, geglu):
+    """producer GEMM accumulates row (sum, sumsq) through stats_out; consumer GEMM applies LayerNorm in its epilogue."""
+    from hallo_b200 import ops
+    dev = _dev()
+    dtype = torch.float16
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a0 = torch.randn(M, 320, generator=g).to(dev, dtype)
+    w0 = (torch.randn(C, 320, generator=g) / 320 ** 0.5).to(dev, dtype)
+    res = (torch.randn(M, C, generator=g) * 2 + 0.7).to(dev, dtype)
+    x = torch.empty(M, C, device=dev, dtype=dtype)
+    stats = torch.zeros(M, 2, device=dev, dtype=torch.float32)
+    ops.gemm(a0, w0, x, residual=res, stats_out=stats)                 # x = a0 w0^T + res, plus row statistics
+    torch.cuda.synchronize()
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (xf * xf).sum(1), rtol=1e-4, atol=1e-2)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev, dtype)
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev, dtype)
+    w = (torch.randn(N, C, generator=g) / C ** 0.5).to(dev, dtype)
+    b = torch.randn(N, generator=g).to(dev, dtype)
+    ref = F.layer_norm(xf, (C,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + b.float()
+    if geglu:
+        wi, bi = ops.pack_geglu_weight(w, b)
+        ref = ref[:, :N // 2] * F.gelu(ref[:, N // 2:])
+    else:
+        wi, bi = w, b
+    wg, colsum, bb = ops.fold_layernorm(wi, bi, gamma, beta, dtype)
+    out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=dtype)
+    ops.gemm(x, wg, out, bias=bb, geglu=geglu, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-5)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 3e-3

@@ -121,3 +121,22 @@ def test_gloo_world2_temporal_gather(tmp_path):
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_layernorm_fold_algebra():
+    """ops.fold_layernorm: rstd * (x W'^T - mu * colsum) + b' == Linear(LayerNorm(x)) (checked in fp32 on the host)."""
+    from hallo_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M, C, N = 37, 64, 48
+    x = torch.randn(M, C, generator=g) * 3 + 1.5
+    w = torch.randn(N, C, generator=g) / 8
+    b = torch.randn(N, generator=g)
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.3 * torch.randn(C, generator=g)
+    wg, cs, bb = ops.fold_layernorm(w, b, gamma, beta, torch.float32)
+    mu = x.mean(1, keepdim=True)
+    var = (x * x).mean(1, keepdim=True) - mu * mu              # the kernel's E[x^2] - mu^2 form
+    rstd = torch.rsqrt(var + 1e-5)
+    out = rstd * (x @ wg.t() - mu * cs[None, :]) + bb
+    ref = F.linear(F.layer_norm(x, (C,), gamma, beta, 1e-5), w, b)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4)
