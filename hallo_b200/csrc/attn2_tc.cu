@@ -269,8 +269,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int i = 0; i < BN; i += 2) {
         const float x0 = fmaf(__uint_as_float(s[i]), p.scale_log2, -m_ref);
         const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_ref);
-        float e0 = (POLY > 0 && (i % POLY) == POLY - 1) ? exp2_poly(x0) : fast_exp2(x0);
-        float e1 = (POLY > 0 && ((i + 1) % POLY) == POLY - 1) ? exp2_poly(x1) : fast_exp2(x1);
+        constexpr int PM = POLY > 0 ? POLY : 1;
+        float e0 = (POLY > 0 && (i % PM) == PM - 1) ? exp2_poly(x0) : fast_exp2(x0);
+        float e1 = (POLY > 0 && ((i + 1) % PM) == PM - 1) ? exp2_poly(x1) : fast_exp2(x1);
         if (tail) {
           if (key0 + i >= p.L) e0 = 0.f;
           if (key0 + i + 1 >= p.L) e1 = 0.f;

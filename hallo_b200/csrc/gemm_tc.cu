@@ -58,6 +58,9 @@ struct GemmDev {
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
 
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_x16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_x32(taddr, r); }
+
 template <int BN, int STAGES, int CG>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
@@ -278,24 +281,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
-      // this warp owns TMEM lanes [32*quarter, +32) and accumulator columns [chalf*BN/2, +BN/2), 16 at a time
+      // this warp owns TMEM lanes [32*quarter, +32) and accumulator columns [chalf*BN/2, +BN/2), CW at a time
+      // (CW = 32 when the half-tile allows it: more independent work per TMEM load for the GELU epilogue)
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
-      constexpr int kChunks = BN / 2 / 16;
-      uint32_t racc[2][16];
-      tmem_ld_x16(taddr, racc[0]);
+      constexpr int CW = ((BN / 2) % 32 == 0) ? 32 : 16;
+      constexpr int kChunks = BN / 2 / CW;
+      uint32_t racc[2][CW];
+      tmem_ld_cw(taddr, racc[0]);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        uint32_t(&r)[16] = racc[c & 1];
-        if (c + 1 < kChunks) tmem_ld_x16(taddr + (c + 1) * 16, racc[(c + 1) & 1]);   // overlaps with this chunk's math
-        const int col0 = tn * BN + chalf * (BN / 2) + c * 16;
+        uint32_t(&r)[CW] = racc[c & 1];
+        if (c + 1 < kChunks) tmem_ld_cw(taddr + (c + 1) * CW, racc[(c + 1) & 1]);   // overlaps with this chunk's math
+        const int col0 = tn * BN + chalf * (BN / 2) + c * CW;
         if (row_ok && col0 < p.N) {
-          float v[16];
+          float v[CW];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
           if (p.ln_stats != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
               if (col0 + j < p.N) {
                 const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + col0 + j);
                 v[j + 0] = ln_rstd * (v[j + 0] - ln_mu * cs.x);
@@ -307,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
+            for (int j = 0; j < CW; j += 8) {
               if (col0 + j < p.N) {
                 float f[8];
                 load8g(bias + col0 + j, f);
@@ -318,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (gb_row != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
+            for (int j = 0; j < CW; j += 8) {
               if (col0 + j < p.N) {
                 float f[8];
                 load8g(gb_row + col0 + j, f);
@@ -329,29 +334,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.flags & HB_EPI_SILU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < CW; ++j) v[j] = silu_f(v[j]);
           }
           if (geglu) {
-            // (value, gate) pairs: 16 accumulator columns -> 8 outputs
+            // (value, gate) pairs: CW accumulator columns -> CW/2 outputs
             const int ocol0 = col0 >> 1;
-            float o[8];
+            float o[CW / 2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
-            if (resid != nullptr) {
-              float f[8];
-              load8g(resid + row * p.ldr + ocol0, f);
+            for (int j = 0; j < CW / 2; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] += f[q];
+            for (int j = 0; j < CW / 2; j += 8) {
+              if (resid != nullptr) {
+                float f[8];
+                load8g(resid + row * p.ldr + ocol0 + j, f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[j + q] += f[q];
+              }
+              uint4 o4;
+              o4.x = Cvt<T>::pack2(o[j + 0], o[j + 1]);
+              o4.y = Cvt<T>::pack2(o[j + 2], o[j + 3]);
+              o4.z = Cvt<T>::pack2(o[j + 4], o[j + 5]);
+              o4.w = Cvt<T>::pack2(o[j + 6], o[j + 7]);
+              *reinterpret_cast<uint4*>(C + row * p.ldc + ocol0 + j) = o4;
             }
-            uint4 o4;
-            o4.x = Cvt<T>::pack2(o[0], o[1]);
-            o4.y = Cvt<T>::pack2(o[2], o[3]);
-            o4.z = Cvt<T>::pack2(o[4], o[5]);
-            o4.w = Cvt<T>::pack2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(C + row * p.ldc + ocol0) = o4;
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
+            for (int j = 0; j < CW; j += 8) {
               if (col0 + j < n_out) {
                 float w[8];
 #pragma unroll
