@@ -719,6 +719,12 @@ extern "C" int hallo_b200_cross_attention(int dtype, const void* Q, int64_t ldq,
       q_region_stride % 8 || kv_region_stride % 8 || o_region_stride % 8)
     return fail(HB_ERR_BAD_SHAPE, "cross_attention: head_dim=%d n_keys=%d", head_dim, n_keys);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // tensor-core path (csrc/xattn_tc.cu) for the layouts the engine produces; CUDA cores otherwise
+    const int r = hb::xattn_tc_try(dtype, Q, ldq, q_region_stride, K, V, ldkv, kv_region_stride, O, ldo, o_region_stride,
+                                   frames, L, heads, head_dim, n_keys, kv_frame_div, regions, s);
+    if (r <= 0) return r;
+  }
   dim3 grid((L + 127) / 128, frames, heads * regions);
   const float sc = (float)(1.4426950408889634 / sqrt((double)head_dim));
   const size_t smem = sizeof(float) * 2 * n_keys * head_dim;

@@ -5,6 +5,7 @@
 #include "attn_tc.cu"
 #include "attn2_tc.cu"
 #include "attn_api.cu"
+#include "xattn_tc.cu"
 #include "aux.cu"
 #include "ubench.cu"
 

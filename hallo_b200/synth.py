@@ -55,6 +55,32 @@ def synth_state_dict(cfg: UNetConfig, seed: int = 0, dtype=torch.float32,
     return sd
 
 
+def synth_state_dict_device(cfg: UNetConfig, device, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Same distributions as synth_state_dict but drawn directly on `device` from one seeded stream (about a
+    second instead of ~15 s per process on the host).  Used by bench.py, where only "random-init weights of the
+    architecture" matters; the parity tests keep the per-key CPU streams so that the oracle sees identical values."""
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape, kind in param_spec(cfg):
+        if kind == "pe":
+            sd[key] = sinusoid_pe(shape[1], shape[2]).to(device)
+        elif kind in ("w", "zero_w"):
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            t = torch.randn(shape, device=device) * (fan_in ** -0.5)
+            sd[key] = t * 0.5 if kind == "zero_w" else t
+        elif kind == "b":
+            sd[key] = torch.randn(shape, device=device) * 0.05
+        elif kind == "norm_w":
+            sd[key] = 1.0 + torch.randn(shape, device=device) * 0.1
+        elif kind == "norm_b":
+            sd[key] = torch.randn(shape, device=device) * 0.1
+        else:
+            raise ValueError(kind)
+    return sd
+
+
 def mask_levels(h: int, w: int):
     """Token counts of the 4 mask scales (image_processor.py:156-180): latent /1,/2,/4,/8."""
     return [(h // s) * (w // s) for s in (1, 2, 4, 8)]

@@ -53,9 +53,12 @@ def layer_norm(sd: SD, name: str, x):
     return F.layer_norm(x, (x.shape[-1],), sd[f"{name}.weight"], sd[f"{name}.bias"], 1e-5)
 
 
+USE_SDPA = False   # bench.py's CPU baseline flips this: same math through torch's fused CPU kernel, like the reference
+
+
 def attention(sd: SD, name: str, x, ctx, heads):
     """diffusers Attention + AttnProcessor2_0: bias-free q/k/v, softmax(qk^T/sqrt d)v,
-    to_out[0] with bias.  Explicit softmax form (independent of F.scaled_dot_product_attention)."""
+    to_out[0] with bias.  Explicit softmax form (independent of F.scaled_dot_product_attention) unless USE_SDPA."""
     q = F.linear(x, sd[f"{name}.to_q.weight"])
     k = F.linear(ctx, sd[f"{name}.to_k.weight"])
     v = F.linear(ctx, sd[f"{name}.to_v.weight"])
@@ -66,8 +69,11 @@ def attention(sd: SD, name: str, x, ctx, heads):
         return t.reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)
 
     q, k, v = split(q), split(k), split(v)
-    p = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-    o = (p @ v).permute(0, 2, 1, 3).reshape(B, Lq, Cq)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B, Lq, Cq)
+    else:
+        p = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+        o = (p @ v).permute(0, 2, 1, 3).reshape(B, Lq, Cq)
     return linear(sd, f"{name}.to_out.0", o)
 
 

@@ -105,11 +105,13 @@ def _sdpa(q, k, v):
     return p @ v
 
 
-@pytest.mark.parametrize("C,nk", [(320, 4), (1280, 4), (320, 32), (640, 32), (1280, 32)])
-def test_cross_attention(C, nk):
+@pytest.mark.parametrize("C,nk,L", [(320, 4, 200), (1280, 4, 200), (320, 32, 200), (640, 32, 200), (1280, 32, 200),
+                                    (320, 32, 1024), (320, 4, 1024), (640, 32, 64)])
+def test_cross_attention(C, nk, L):
+    """L >= 128 runs the tcgen05 kernel (csrc/xattn_tc.cu), smaller L the CUDA-core kernel."""
     from hallo_b200 import ops
     dev = _dev()
-    H, frames, L, f = 8, 4, 200, 2
+    H, frames, f = 8, 4, 2
     d = C // H
     regions = 3 if nk == 32 else 1
     div = f if nk == 4 else 1
