@@ -569,7 +569,15 @@ class DenoiseEngine:
         """CFG combine + DDIM update + step counter (face_animate.py:415-420)."""
         sh = self.shard
         mo = self.model_out
-        if self.nb == 1:
+        if self.nb == 1 and sh.world_size == 1:
+            # profiling aid (bench.py --emulate-shard): one rank's workload without its peer; the combine sees the same
+            # half twice, which keeps the kernel sequence and shapes of a real rank
+            n = mo.shape[0]
+            both = self.buf("out.both", 2 * n, mo.shape[1])
+            both[:n].copy_(mo)
+            both[n:].copy_(mo)
+            mo = both
+        elif self.nb == 1:
             # the two CFG halves live on different ranks: exchange the (tiny) model outputs
             import torch.distributed as dist
             allm = self.buf("out.all", sh.world_size * mo.shape[0], mo.shape[1])
