@@ -6,12 +6,20 @@ namespace hb {
 
 template <typename T>
 static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
-  static const bool v1 = getenv("HALLO_B200_ATTN_V1") != nullptr;   // A/B switches for benchmarking
-  static const int poly = getenv("HALLO_B200_ATTN_POLY") ? atoi(getenv("HALLO_B200_ATTN_POLY")) : 0;
+  const bool v1 = option(OPT_ATTN_V1) != 0;     // A/B switches (hallo_b200_set_option / HALLO_B200_ATTN_*)
+  const int poly = option(OPT_ATTN_POLY);
+  // streamed softmax (attn2_tc.cu, CHUNK = 32): written after the last GPU session of round 1, so it stays
+  // opt-in until tests/test_attention_gpu.py has passed with attn_chunk = 1 on hardware
+  const bool chunk = option(OPT_ATTN_CHUNK) != 0;
   switch (p->head_dim) {
     // v2 (two query tiles per CTA, P in TMEM) when a frame has at least one full pair of tiles; the
     // single-tile kernel otherwise (small L) and for head_dim 160 at small L.
     case 40:
+      if (p->L >= 256 && !v1 && chunk) {
+        if (poly == 4) return launch_attn2<T, 40, 128, 4, 32>(p, s);
+        if (poly == 3) return launch_attn2<T, 40, 128, 3, 32>(p, s);
+        return launch_attn2<T, 40, 128, 0, 32>(p, s);
+      }
       if (p->L >= 256 && !v1) {
         if (poly == 4) return launch_attn2<T, 40, 128, 4>(p, s);
         if (poly == 3) return launch_attn2<T, 40, 128, 3>(p, s);
@@ -20,6 +28,7 @@ static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
       }
       return launch_attn<T, 40, 128, 2>(p, s);
     case 80:
+      if (p->L >= 256 && !v1 && chunk) return launch_attn2<T, 80, 128, 0, 32>(p, s);
       if (p->L >= 256 && !v1) return launch_attn2<T, 80, 128, 0>(p, s);
       return launch_attn<T, 80, 64, 2>(p, s);
     case 160: return launch_attn<T, 160, 64, 2>(p, s);   // 2 x (2 S buffers + O) does not fit TMEM at d = 160

@@ -61,20 +61,35 @@ struct GemmDev {
 __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_x16(taddr, r); }
 __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_x32(taddr, r); }
 
-template <int BN, int STAGES, int CG>
+constexpr int kPanelCols = 32;                        // output columns per staged panel (TMA-store epilogue)
+constexpr int kPanelBytes = kBM * kPanelCols * 2;     // 128 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B
+constexpr int kEpiBufs = 3;                           // panel buffers per warp group: store in flight | being written | residual landing
+
+template <int BN, int STAGES, int CG, bool TEPI = false>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;   // a CTA of a pair stages half of the W rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kStgOffset = STAGES * kStageBytes;                 // TEPI: 2 warp groups x kEpiBufs panel buffers
+  static constexpr int kBarOffset = kStgOffset + (TEPI ? 2 * kEpiBufs * kPanelBytes : 0);
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static_assert(kStageBytes % 1024 == 0, "stage alignment");
 };
 
-template <typename T, int BN, int STAGES, bool CONV, int CG>
+// TEPI: epilogue through shared memory and TMA.  The direct epilogue has every lane own one output ROW, so each
+// 16-byte store (and residual load) of a warp touches 32 different 128-byte lines: ~BN*16 LSU wavefronts per
+// tile for the stores and as many for the residual, against BN*K/32 clk of MMA -- the K <= 640 GEMMs that make
+// up most of the step are bound by it (cuBLAS is 1.25-1.5x faster on those shapes,
+// profiles/r1_kbench_gemm_staged_epilogue_regression.log).  With TEPI the two groups of 4 epilogue warps write
+// 128 x 32 output panels into swizzled shared memory (conflict-free), an elected thread stores each panel with
+// one cp.async.bulk.tensor (clipped at the tensor edge, so no row masks) and the residual panel is prefetched
+// by TMA into the same buffer two panels ahead.
+template <typename T, int BN, int STAGES, bool CONV, int CG, bool TEPI = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using SM = GemmSmem<BN, STAGES, CG>;
+               const __grid_constant__ CUtensorMap tmB, const GemmDev p,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR) {
+  using SM = GemmSmem<BN, STAGES, CG, TEPI>;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int cta_stride = gridDim.x / CG;          // persistent loop stride in units of (pairs of) CTAs
@@ -90,7 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;      // TEPI: residual panel landed, [group][buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +115,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.K1 < p.K) tma_prefetch_desc(&tmA2);
+    if (TEPI) {
+      tma_prefetch_desc(&tmC);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -109,6 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8 * CG);  // pair: the epilogue warps of both CTAs release the leader's accumulator
     }
+    if (TEPI)
+      for (int s = 0; s < 2 * kEpiBufs; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -228,6 +250,240 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (TEPI) {
+    // ===================== epilogue warps, shared-memory staged + TMA stores =====================
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;     // group of 4 warps; takes output panels grp, grp + 2, ...
+    const bool elected = (quarter == 0 && lane == 0);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* gbias = reinterpret_cast<const T*>(p.group_bias);
+    const T* rscale = reinterpret_cast<const T*>(p.row_scale);
+    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    const bool has_res = p.residual != nullptr;
+    // a unit = 32 accumulator columns (one TMEM load); a panel = 32 output columns = 1 unit (2 with GEGLU)
+    constexpr int kMaxUnits = (BN % 64 == 0) ? 2 * ((BN / 64 + 1) / 2) : (BN / 32 + 1) / 2;
+    const int panels = (geglu ? BN / 64 : BN / 32);
+    const int my_panels = (panels - grp + 1) / 2;
+    const int my_units = geglu ? 2 * my_panels : my_panels;
+    const int out_bn = geglu ? BN / 2 : BN;                      // output columns per tile
+    uint8_t* stg = smem + SM::kStgOffset + grp * (kEpiBufs * kPanelBytes);
+    uint64_t* res_full = res_bar + grp * kEpiBufs;
+    const int r_in_tile = quarter * 32 + lane;
+    // panel buffer = 128 rows of 64 B, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk c of row r sits at
+    // r*64 + ((c ^ ((r >> 1) & 3)) << 4); the 8 rows of a quarter-warp phase hit 8 different bank groups
+    const uint32_t row_off = (uint32_t)r_in_tile * 64u;
+    const uint32_t row_sw = ((uint32_t)r_in_tile >> 1) & 3u;
+
+    auto tile_origin = [&](int t, int& tm, int& tn, int& n0, int& h0, int& w0) {
+      tm = (t / p.tiles_n) * CG + (int)rank;
+      tn = t % p.tiles_n;
+      n0 = h0 = w0 = 0;
+      if (CONV) {
+        const int per_img = p.tiles_w * p.tiles_h;
+        const int nb = tm / per_img;
+        const int rem = tm - nb * per_img;
+        const int hb_ = rem / p.tiles_w;
+        n0 = nb * p.box_n;
+        h0 = hb_ * p.box_h;
+        w0 = (rem - hb_ * p.tiles_w) * p.box_w;
+      }
+    };
+    // residual prefetch iterator (elected thread only): the next (tile, panel) of this group to request
+    int pf_t = cta_first, pf_i = 0, pf_b = 0;
+    auto prefetch_residual = [&]() {
+      if (pf_t >= num_tiles) return;
+      int tm, tn, n0, h0, w0;
+      tile_origin(pf_t, tm, tn, n0, h0, w0);
+      const int ocol = tn * out_bn + (grp + 2 * pf_i) * kPanelCols;
+      mbar_arrive_expect_tx(&res_full[pf_b], kPanelBytes);
+      if (CONV) tma_load_4d(stg + pf_b * kPanelBytes, &tmR, &res_full[pf_b], ocol, w0, h0, n0);
+      else tma_load_2d(stg + pf_b * kPanelBytes, &tmR, &res_full[pf_b], ocol, tm * kBM);
+      if (++pf_b == kEpiBufs) pf_b = 0;
+      if (++pf_i == my_panels) {
+        pf_i = 0;
+        pf_t += cta_stride;
+      }
+    };
+    // panel q of this group lives in buffer q % kEpiBufs.  At the end of panel q the elected thread issues
+    // store(q) and waits only until store(q-1) has been READ (issued a whole panel earlier), which frees buffer
+    // (q-1) % kEpiBufs for the residual of panel q + kEpiBufs - 1: the residual runs kEpiBufs - 1 panels ahead.
+    if (has_res && elected) {
+      for (int i = 0; i < kEpiBufs - 1; ++i) prefetch_residual();
+    }
+    __syncwarp();
+
+    int b = 0;                            // buffer of the current panel
+    uint32_t bphase = 0;                  // parity of res_full[b] for the current round through the buffers
+    int it = 0;
+    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
+      int tm, tn, n0, h0, w0;
+      tile_origin(t, tm, tn, n0, h0, w0);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      long long row;
+      bool row_ok;
+      if (CONV) {
+        const int dn = r_in_tile / (p.box_h * p.box_w);
+        const int r2 = r_in_tile - dn * (p.box_h * p.box_w);
+        const int dh = r2 / p.box_w;
+        const int dw = r2 - dh * p.box_w;
+        const int in_ = n0 + dn, ih = h0 + dh, iw = w0 + dw;
+        row = ((long long)in_ * p.img_h + ih) * p.img_w + iw;
+        row_ok = in_ < p.img_n && ih < p.img_h && iw < p.img_w;   // overhanging rows are clipped by the TMA store
+      } else {
+        row = (long long)tm * kBM + r_in_tile;
+        row_ok = row < p.M;
+      }
+      float rs = p.alpha;
+      if (rscale != nullptr && row_ok) rs *= Cvt<T>::to_f(rscale[row]);
+      const T* gb_row = nullptr;
+      if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr && row_ok) {
+        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * row);
+        ln_mu = st.x / (float)p.K;
+        const float var = fmaxf(st.y / (float)p.K - ln_mu * ln_mu, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+      }
+      float osum = 0.f, osq = 0.f;
+
+      mbar_wait(&tfull_bar[as], aphase, 0x31);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
+      // accumulator column of unit u: plain -> panel (grp + 2u); GEGLU -> panel (grp + 2(u/2)), half (u & 1)
+      auto unit_col = [&](int u) { return geglu ? (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 : (grp + 2 * u) * 32; };
+      uint32_t racc[2][32];
+      tmem_ld_x32(taddr + unit_col(0), racc[0]);
+#pragma unroll
+      for (int u = 0; u < kMaxUnits; ++u) {
+        if (u >= my_units) break;
+        tmem_ld_wait();
+        uint32_t(&r)[32] = racc[u & 1];
+        if (u + 1 < my_units) tmem_ld_x32(taddr + unit_col(u + 1), racc[(u + 1) & 1]);   // overlaps with the math below
+        const int acol0 = tn * BN + unit_col(u);                   // first accumulator (= weight row) column
+        const bool first_of_panel = !geglu || (u & 1) == 0;
+        const bool last_of_panel = !geglu || (u & 1) == 1;
+        uint8_t* sbuf = stg + b * kPanelBytes;
+        const uint32_t sbuf_u32 = smem_u32(sbuf);
+        if (first_of_panel && has_res) mbar_wait(&res_full[b], bphase, 0x33);
+
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.ln_stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + acol0 + j);
+            v[j + 0] = ln_rstd * (v[j + 0] - ln_mu * cs.x);
+            v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * cs.y);
+            v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * cs.z);
+            v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * cs.w);
+          }
+        }
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+            load8g(bias + acol0 + j, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[j + k] += f[k];
+          }
+        }
+        if (gb_row != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+            load8g(gb_row + acol0 + j, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[j + k] += f[k];
+          }
+        }
+        if (p.flags & HB_EPI_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        }
+        if (geglu) {
+          // (value, gate) pairs: 32 accumulator columns -> 16 outputs = chunks 2*(u&1), 2*(u&1)+1 of the panel row
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t cell = sbuf_u32 + row_off + ((((uint32_t)((u & 1) * 2 + c)) ^ row_sw) << 4);
+            if (has_res) {
+              const uint4 rv = lds128(cell);
+              const float2 a0 = Cvt<T>::unpack2(rv.x), a1 = Cvt<T>::unpack2(rv.y), a2 = Cvt<T>::unpack2(rv.z),
+                           a3 = Cvt<T>::unpack2(rv.w);
+              o[c * 8 + 0] += a0.x; o[c * 8 + 1] += a0.y; o[c * 8 + 2] += a1.x; o[c * 8 + 3] += a1.y;
+              o[c * 8 + 4] += a2.x; o[c * 8 + 5] += a2.y; o[c * 8 + 6] += a3.x; o[c * 8 + 7] += a3.y;
+            }
+            uint4 o4;
+            o4.x = Cvt<T>::pack2(o[c * 8 + 0], o[c * 8 + 1]);
+            o4.y = Cvt<T>::pack2(o[c * 8 + 2], o[c * 8 + 3]);
+            o4.z = Cvt<T>::pack2(o[c * 8 + 4], o[c * 8 + 5]);
+            o4.w = Cvt<T>::pack2(o[c * 8 + 6], o[c * 8 + 7]);
+            sts128(cell, o4);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t cell = sbuf_u32 + row_off + ((((uint32_t)c) ^ row_sw) << 4);
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = v[c * 8 + k] * rs;
+            if (has_res) {
+              const uint4 rv = lds128(cell);
+              const float2 a0 = Cvt<T>::unpack2(rv.x), a1 = Cvt<T>::unpack2(rv.y), a2 = Cvt<T>::unpack2(rv.z),
+                           a3 = Cvt<T>::unpack2(rv.w);
+              w[0] += a0.x; w[1] += a0.y; w[2] += a1.x; w[3] += a1.y;
+              w[4] += a2.x; w[5] += a2.y; w[6] += a3.x; w[7] += a3.y;
+            }
+            uint4 o4;
+            o4.x = Cvt<T>::pack2(w[0], w[1]);
+            o4.y = Cvt<T>::pack2(w[2], w[3]);
+            o4.z = Cvt<T>::pack2(w[4], w[5]);
+            o4.w = Cvt<T>::pack2(w[6], w[7]);
+            sts128(cell, o4);
+            if (p.stats_out != nullptr) {
+              // statistics of the values as the next LayerNorm will read them (rounded to the storage type)
+              const float2 q0 = Cvt<T>::unpack2(o4.x), q1 = Cvt<T>::unpack2(o4.y), q2 = Cvt<T>::unpack2(o4.z),
+                           q3 = Cvt<T>::unpack2(o4.w);
+              osum += (q0.x + q0.y) + (q1.x + q1.y) + (q2.x + q2.y) + (q3.x + q3.y);
+              osq += (q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y) + (q2.x * q2.x + q2.y * q2.y) +
+                     (q3.x * q3.x + q3.y * q3.y);
+            }
+          }
+        }
+        if (last_of_panel) {
+          fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            const int ocol = tn * out_bn + (geglu ? (grp + 2 * (u >> 1)) : (grp + 2 * u)) * kPanelCols;
+            if (CONV) tma_store_4d(&tmC, sbuf, ocol, w0, h0, n0);
+            else tma_store_2d(&tmC, sbuf, ocol, tm * kBM);
+            bulk_commit_group();
+            bulk_wait_group_read<1>();                    // the previous panel's buffer is free again ...
+            if (has_res) prefetch_residual();             // ... and takes the residual of panel q + kEpiBufs - 1
+          }
+          __syncwarp();
+          if (++b == kEpiBufs) {
+            b = 0;
+            bphase ^= 1u;
+          }
+        }
+      }
+      if (p.stats_out != nullptr && row_ok) {
+        atomicAdd(p.stats_out + 2 * row, osum);
+        atomicAdd(p.stats_out + 2 * row + 1, osq);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && !leader) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
+    }
+    if (elected) bulk_wait_group<0>();      // global writes of the last panels performed before the CTA retires
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -431,9 +687,9 @@ static void pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
     }
 }
 
-template <typename T, int BN, int STAGES, int CG>
+template <typename T, int BN, int STAGES, int CG, bool TEPI = false>
 static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
-  using SM = GemmSmem<BN, STAGES, CG>;
+  using SM = GemmSmem<BN, STAGES, CG, TEPI>;
   static_assert(SM::kTotal <= 232448, "gemm smem budget");
   GemmDev d{};
   d.M = q->M;
@@ -506,11 +762,35 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
     }
   }
 
+  // output / residual maps of the TMA-store epilogue: 128-row x 32-column panels (conv: the same NHWC box as A)
+  CUtensorMap tmC = tmA, tmR = tmA;
+  if (TEPI) {
+    const uint64_t n_out = (q->flags & HB_EPI_GEGLU) ? (uint64_t)q->N / 2 : (uint64_t)q->N;
+    for (int which = 0; which < 2; ++which) {
+      const void* base = which == 0 ? q->C : q->residual;
+      const uint64_t ld = which == 0 ? (uint64_t)q->ldc : (uint64_t)q->ldr;
+      if (base == nullptr) continue;
+      CUtensorMap* out = which == 0 ? &tmC : &tmR;
+      if (q->conv3x3) {
+        uint64_t dims[4] = {n_out, (uint64_t)q->img_w, (uint64_t)q->img_h, (uint64_t)q->img_n};
+        uint64_t str[3] = {ld * 2, ld * 2 * q->img_w, ld * 2 * q->img_w * q->img_h};
+        uint32_t box[4] = {kPanelCols, (uint32_t)d.box_w, (uint32_t)d.box_h, (uint32_t)d.box_n};
+        if ((rc = make_tmap_16b(out, q->dtype, base, 4, dims, str, box, 64)) != HB_OK) return rc;
+      } else {
+        uint64_t dims[2] = {n_out, (uint64_t)q->M};
+        uint64_t str[1] = {ld * 2};
+        uint32_t box[2] = {kPanelCols, kBM};
+        if ((rc = make_tmap_16b(out, q->dtype, base, 2, dims, str, box, 64)) != HB_OK) return rc;
+      }
+    }
+  }
+
   const int tiles = ((d.tiles_m + CG - 1) / CG) * d.tiles_n;      // (pairs of) tiles
   if (tiles <= 0) return HB_OK;
   const int max_ctas = num_sms() / CG;
   const int grid = (tiles < max_ctas ? tiles : max_ctas) * CG;
-  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true, CG> : gemm_tc_kernel<T, BN, STAGES, false, CG>;
+  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true, CG, TEPI>
+                         : gemm_tc_kernel<T, BN, STAGES, false, CG, TEPI>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[q->conv3x3 ? 1 : 0]) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
@@ -528,16 +808,26 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, d));
+  HB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, d, tmC, tmR));
   HB_LAUNCH_CHECK();
   return HB_OK;
 }
 
 template <typename T>
 static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
-  static const bool force1 = getenv("HALLO_B200_GEMM_1CTA") != nullptr;     // A/B switch for benchmarking
+  const bool force1 = option(OPT_GEMM_1CTA) != 0;     // A/B switch for benchmarking
   const int tiles_m = p->conv3x3 ? 2 : (p->M + kBM - 1) / kBM;
   if (force1 || tiles_m < 2) return launch_gemm<T, 160, 5, 1>(p, s);
+  // TMA-store epilogue (TEPI): written after the last GPU session of round 1 -> opt-in until tests/test_gemm_gpu.py
+  // has passed with gemm_tepi = 1 on hardware.  Needs whole N tiles and 16-byte aligned C / residual.
+  const bool tepi_env = option(OPT_GEMM_TEPI) != 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p->C) | reinterpret_cast<uintptr_t>(p->residual)) & 15) == 0;
+  if (tepi_env && aligned) {
+    const bool geglu = (p->flags & HB_EPI_GEGLU) != 0;
+    if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
+    if (p->N % 192 == 0) return launch_gemm<T, 192, 6, 2, true>(p, s);
+    if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
+  }
   // widest N tile that divides N: fewer shared-memory bytes per MMA flop (see the header comment)
   if (p->N % 256 == 0) return launch_gemm<T, 256, 6, 2>(p, s);
   if (p->N % 192 == 0) return launch_gemm<T, 192, 7, 2>(p, s);

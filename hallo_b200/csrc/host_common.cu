@@ -1,11 +1,48 @@
 #include "host_common.cuh"
 
+#include <cctype>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace hb {
 
 char g_last_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
+
+static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc"};
+static std::atomic<int> g_options[OPT_COUNT];
+static std::atomic<bool> g_options_init{false};
+
+static void init_options() {
+  if (g_options_init.load(std::memory_order_acquire)) return;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (g_options_init.load(std::memory_order_relaxed)) return;
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    char env[64] = "HALLO_B200_";
+    size_t n = strlen(env);
+    for (const char* c = kOptionNames[i]; *c && n + 1 < sizeof(env); ++c) env[n++] = (char)toupper((unsigned char)*c);
+    env[n] = 0;
+    const char* v = getenv(env);
+    // a variable that is set but empty or non-numeric counts as 1 (the historical "defined = on" switches)
+    int val = 0;
+    if (v != nullptr) val = (*v >= '0' && *v <= '9') ? atoi(v) : 1;
+    g_options[i].store(val, std::memory_order_relaxed);
+  }
+  g_options_init.store(true, std::memory_order_release);
+}
+
+int option(Option o) {
+  init_options();
+  return g_options[o].load(std::memory_order_relaxed);
+}
+static int find_option(const char* name) {
+  if (name == nullptr) return -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptionNames[i]) == 0) return i;
+  return -1;
+}
 
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -19,7 +56,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box) {
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -42,8 +79,12 @@ int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const
   }
   CUtensorMapDataType dt =
       dtype == HB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  if (swizzle_bytes != 128 && swizzle_bytes != 64) return fail(HB_ERR_BAD_SHAPE, "tmap swizzle %d", swizzle_bytes);
+  if ((uint64_t)box[0] * 2 > (uint64_t)swizzle_bytes)
+    return fail(HB_ERR_BAD_SHAPE, "tmap inner box %u x 2 B exceeds the %d B swizzle span", box[0], swizzle_bytes);
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(HB_ERR_CUDA,
@@ -62,6 +103,19 @@ extern "C" {
 int hallo_b200_abi_version(void) { return 1; }
 
 const char* hallo_b200_last_error(void) { return hb::g_last_error; }
+
+int hallo_b200_set_option(const char* name, int value) {
+  hb::init_options();
+  const int i = hb::find_option(name);
+  if (i < 0) return hb::fail(HB_ERR_BAD_SHAPE, "hallo_b200_set_option: unknown option '%s'", name ? name : "(null)");
+  hb::g_options[i].store(value, std::memory_order_relaxed);
+  return HB_OK;
+}
+int hallo_b200_get_option(const char* name) {
+  hb::init_options();
+  const int i = hb::find_option(name);
+  return i < 0 ? -1 : hb::g_options[i].load(std::memory_order_relaxed);
+}
 
 int64_t hallo_b200_launch_count(int reset) {
   int64_t v = hb::g_launch_count.load();

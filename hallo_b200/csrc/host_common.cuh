@@ -15,6 +15,10 @@ namespace hb {
 extern char g_last_error[512];
 extern std::atomic<int64_t> g_launch_count;
 
+// run-time kernel-selection switches (hallo_b200_set_option); initial value from HALLO_B200_<NAME>
+enum Option { OPT_GEMM_TEPI = 0, OPT_GEMM_1CTA, OPT_ATTN_CHUNK, OPT_ATTN_POLY, OPT_ATTN_V1, OPT_XATTN_TC, OPT_COUNT };
+int option(Option o);
+
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -50,7 +54,7 @@ PFN_encodeTiled get_encode_tiled();
 // rank-R tiled tensor map over 16-bit elements, 128B swizzle, zero OOB fill.
 // dims/strides innermost first; strides_bytes has rank-1 entries (dims 1..R-1).
 int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box);
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 inline int num_sms() {
   static int n = 0;

@@ -317,8 +317,8 @@ int xattn_tc_try(int dtype, const void* Q, long long ldq, int q_region_stride, c
                  long long ldkv, int kv_region_stride, void* O, long long ldo, int o_region_stride, int frames, int L,
                  int heads, int head_dim, int n_keys, int kv_frame_div, int regions, cudaStream_t s) {
   // Opt-in until it has been parity-tested on hardware (written after the round-1 GPU budget was spent):
-  // HALLO_B200_XATTN_TC=1 routes eligible shapes here; default is the tested CUDA-core kernel in aux.cu.
-  static const bool off = getenv("HALLO_B200_XATTN_TC") == nullptr;
+  // xattn_tc = 1 (HALLO_B200_XATTN_TC) routes eligible shapes here; default is the tested CUDA-core kernel in aux.cu.
+  const bool off = option(OPT_XATTN_TC) == 0;
   const int C = heads * head_dim;
   // layout contract of this kernel: Q regions C apart, [K_r | V_r] pairs 2C apart with V = K + C columns, n_keys <= 32
   if (off || (head_dim != 40 && head_dim != 80 && head_dim != 160) || n_keys > 32 || n_keys < 1 || L < 128) return 1;

@@ -71,6 +71,8 @@ def load() -> C.CDLL:
     lib.hallo_b200_launch_count.restype = C.c_int64
     lib.hallo_b200_launch_count.argtypes = [C.c_int]
     lib.hallo_b200_device_error.argtypes = [C.POINTER(C.c_uint)]
+    lib.hallo_b200_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.hallo_b200_get_option.argtypes = [C.c_char_p]
     _lib = lib
     return lib
 
@@ -101,6 +103,18 @@ def current_stream() -> C.c_void_p:
 
 def launch_count(reset: bool = False) -> int:
     return int(load().hallo_b200_launch_count(1 if reset else 0))
+
+
+def set_option(name: str, value: int) -> None:
+    """Kernel-selection switch (include/hallo_b200.h: hallo_b200_set_option); read at launch / graph-capture time."""
+    check(load().hallo_b200_set_option(name.encode(), int(value)), f"set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = int(load().hallo_b200_get_option(name.encode()))
+    if v < 0:
+        raise KeyError(name)
+    return v
 
 
 def device_error() -> int:

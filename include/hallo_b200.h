@@ -46,6 +46,17 @@ const char* hallo_b200_last_error(void);
 int hallo_b200_device_error(unsigned int* code_out);
 /* Number of kernel launches issued by this library since the last reset (bench.py gpu_launches). */
 int64_t hallo_b200_launch_count(int reset);
+/* Kernel-selection switches (A/B benchmarking and staged roll-out of new kernels; results are identical up to
+ * rounding whatever the setting).  Each option starts from the environment variable HALLO_B200_<NAME> (upper
+ * case) and can be changed at run time; unknown names return HB_ERR_BAD_SHAPE / -1.
+ *   "gemm_tepi"   1: GEMM / conv epilogue staged through shared memory and written by TMA stores  (default 0)
+ *   "gemm_1cta"   1: force the single-CTA GEMM kernel                                              (default 0)
+ *   "attn_chunk"  1: attention streams S through registers in 32-column chunks                     (default 0)
+ *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU            (default 0)
+ *   "attn_v1"     1: force the first-generation attention kernel                                   (default 0)
+ *   "xattn_tc"    1: tcgen05 cross-attention instead of the CUDA-core kernel                       (default 0) */
+int hallo_b200_set_option(const char* name, int value);
+int hallo_b200_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------
  * hallo_b200_gemm -- C = epilogue(A * W^T) on tcgen05 tensor cores, TMA-fed, TMEM accumulators.

@@ -26,6 +26,24 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert lib.hallo_b200_abi_version() == 1
 
 
+def test_kernel_selection_options_roundtrip():
+    """hallo_b200_set_option / get_option are host-only: defaults keep every hardware-untested kernel switched off."""
+    import __graft_entry__ as g
+    g.build()
+    from hallo_b200 import lib
+    for name in ("gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc"):
+        if os.environ.get("HALLO_B200_" + name.upper()) is None:
+            assert lib.get_option(name) == 0, name
+        old = lib.get_option(name)
+        lib.set_option(name, 3)
+        assert lib.get_option(name) == 3
+        lib.set_option(name, old)
+    with pytest.raises(RuntimeError):
+        lib.set_option("no_such_option", 1)
+    with pytest.raises(KeyError):
+        lib.get_option("no_such_option")
+
+
 def test_no_cpu_fallback_in_product_path():
     """The product must fail loudly without CUDA, and must not import the oracle."""
     from hallo_b200.models.unet_3d import UNet3DConditionModel

@@ -56,6 +56,11 @@ def bench_gemm():
         out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.float16)
         ms = timeit(lambda: ops.gemm(a, w, out, geglu=geglu))
         report(f"gemm M{M} N{N} K{K}{' geglu' if geglu else ''}", ms, 2.0 * M * N * K)
+        if not geglu and N <= 1280:
+            res = torch.randn(M, N, device=dev, dtype=torch.float16)
+            bias = torch.randn(N, device=dev, dtype=torch.float16)
+            ms = timeit(lambda: ops.gemm(a, w, out, bias=bias, residual=res))
+            report(f"gemm M{M} N{N} K{K} +bias+residual", ms, 2.0 * M * N * K)
         ms = timeit(lambda: torch.matmul(a, w.t()))
         report(f"  cublas same shape", ms, 2.0 * M * N * K)
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Parity + speed of the opt-in kernels (include/hallo_b200.h: hallo_b200_set_option), one process per switch so a
+# trapping kernel only takes its own run down.  Run on the GPU box:  bash tools/run_experimental.sh
+# Logs land in gpurun_out/exp_*.log; promote a switch to default only when its parity run is green AND faster.
+mkdir -p gpurun_out
+: > gpurun_out/exp_summary.txt
+run() {   # name, env assignment, test files...
+  local name=$1 envs=$2; shift 2
+  env $envs timeout 900 python -m pytest "$@" -q -m gpu -x -p no:cacheprovider > gpurun_out/exp_${name}_tests.log 2>&1
+  echo "$name tests exit $?" | tee -a gpurun_out/exp_summary.txt
+}
+run gemm_tepi  HALLO_B200_GEMM_TEPI=1  tests/test_gemm_gpu.py tests/test_aux_gpu.py tests/test_unet_gpu.py
+run attn_chunk HALLO_B200_ATTN_CHUNK=1 tests/test_attention_gpu.py tests/test_unet_gpu.py
+run xattn_tc   HALLO_B200_XATTN_TC=1   tests/test_aux_gpu.py tests/test_unet_gpu.py
+# speed: baseline first, then each switch
+timeout 600 python tools/kbench.py gemm conv attn > gpurun_out/exp_kbench_base.log 2>&1
+HALLO_B200_GEMM_TEPI=1 timeout 600 python tools/kbench.py gemm conv > gpurun_out/exp_kbench_gemm_tepi.log 2>&1
+HALLO_B200_ATTN_CHUNK=1 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk.log 2>&1
+HALLO_B200_ATTN_CHUNK=1 HALLO_B200_ATTN_POLY=4 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk_poly4.log 2>&1
+tail -n 30 gpurun_out/exp_kbench_*.log >> gpurun_out/exp_summary.txt
+cat gpurun_out/exp_summary.txt
