@@ -19,11 +19,18 @@ def test_c_abi_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "hallo_b200.h")).read()
     names = sorted(set(re.findall(r"\b(hallo_b200_[a-z0-9_]+)\s*\(", hdr)))
     assert len(names) >= 15
-    lib = ctypes.CDLL(os.path.join(ROOT, "hallo_b200", "libhallo_b200.so"))
-    missing = [n for n in names if not hasattr(lib, n)]
+    cdll = ctypes.CDLL(os.path.join(ROOT, "hallo_b200", "libhallo_b200.so"))
+    missing = [n for n in names if not hasattr(cdll, n)]
     assert not missing, missing
-    lib.hallo_b200_abi_version.restype = ctypes.c_int
-    assert lib.hallo_b200_abi_version() == 1
+    cdll.hallo_b200_abi_version.restype = ctypes.c_int
+    assert cdll.hallo_b200_abi_version() == 1
+
+
+def test_no_undefined_names_in_gpu_only_code():
+    """GPU-only branches (tests marked gpu, bench.py, the engine) cannot run here; at least every global name they
+    load must be bound (a missing import in a GPU test fixture would otherwise only surface on the box)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "lint_names.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
 
 
 def test_kernel_selection_options_roundtrip():

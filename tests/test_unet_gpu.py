@@ -24,7 +24,7 @@ def _dev():
 def model():
     from hallo_b200.models.unet_3d import UNet3DConditionModel
     from hallo_b200.spec import HALLO_UNET_KWARGS, SD15_UNET_CONFIG, UNetConfig
-    from hallo_b200.synth import synth_state_dict
+    from hallo_b200.synth import host_threads, synth_state_dict
     dev = _dev()
     torch.set_num_threads(host_threads())
     sd = synth_state_dict(UNetConfig(), seed=0)
