@@ -182,7 +182,12 @@ def main():
     dt = torch.float16
     from hallo_b200.synth import host_threads
     torch.set_num_threads(max(1, host_threads() // world))
-    sd = synth_state_dict_device(cfg, dev, seed=0)       # random-init weights, drawn on the GPU (identical on every rank)
+    try:
+        sd = synth_state_dict_device(cfg, dev, seed=0)   # random-init weights, drawn on the GPU (identical on every rank)
+    except Exception as e:                               # set-up only: same distributions from the host streams
+        print(f"# rank {rank}: on-device weight synthesis failed ({type(e).__name__}: {e}); drawing on the host", file=sys.stderr)
+        from hallo_b200.synth import synth_state_dict
+        sd = synth_state_dict(cfg, seed=0)
     W = PackedWeights(sd, cfg, dev, dt)
     del sd
     inp = synth_inputs(cfg, args.size, args.size, args.frames, seed=42)

@@ -751,6 +751,10 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
     return fail(HB_ERR_BAD_SHAPE, "temporal_attention: head_dim=%d Fk=%d", head_dim, Fk);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {
+    const int rc = hb::tattn_mma_try(dtype, Q, ldq, K, V, ldkv, O, ldo, batch, Fq, Fk, L, heads, head_dim, s);
+    if (rc != 1) return rc;      // handled (or failed) by the tensor-core kernel; 1 = not enabled / not eligible
+  }
+  {
     // shared-memory variant when one pixel's threads fit a CTA and its K/V rows fit shared memory
     const int C = heads * head_dim;
     const int per_pix = heads * Fq;

@@ -6,6 +6,7 @@
 #include "attn2_tc.cu"
 #include "attn_api.cu"
 #include "xattn_tc.cu"
+#include "tattn_mma.cu"
 #include "aux.cu"
 #include "ubench.cu"
 

@@ -84,7 +84,7 @@ class PackedWeights:
         # stem / head
         w_in = sd["conv_in.weight"]                                  # [C0, Cl, 3, 3] -> [C0, 64], k = tap*Cl + c
         c0, cl = w_in.shape[0], w_in.shape[1]
-        wi = torch.zeros(c0, 64, dtype=w_in.dtype)
+        wi = torch.zeros(c0, 64, dtype=w_in.dtype, device=w_in.device)
         wi[:, :9 * cl] = w_in.permute(0, 2, 3, 1).reshape(c0, 9 * cl)
         put("conv_in.w", wi)
         put("conv_in.b", sd["conv_in.bias"])
@@ -92,9 +92,9 @@ class PackedWeights:
         lin("time_embedding.linear_2")
         norm("conv_norm_out")
         w_out = ops.pack_conv3x3_weight(sd["conv_out.weight"])       # [Cl, 9*C0] -> padded to 8 rows
-        wo = torch.zeros(8, w_out.shape[1], dtype=w_out.dtype)
+        wo = torch.zeros(8, w_out.shape[1], dtype=w_out.dtype, device=w_out.device)
         wo[:w_out.shape[0]] = w_out
-        bo = torch.zeros(8, dtype=w_out.dtype)
+        bo = torch.zeros(8, dtype=w_out.dtype, device=w_out.device)
         bo[:w_out.shape[0]] = sd["conv_out.bias"]
         put("conv_out.w", wo)
         put("conv_out.b", bo)

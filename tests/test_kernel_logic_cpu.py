@@ -1,0 +1,207 @@
+"""CPU checks of kernel-side index / algorithm logic that can be restated without a GPU:
+ * the lane-level fragment arithmetic of hallo_b200/csrc/tattn_mma.cu (ldmatrix / mma.sync m16n8k16 layouts per the
+   PTX ISA) reproduces softmax(Q K^T / sqrt(d)) V for every (pixel, head) task, including ragged frame counts, the
+   half-filled last k-step of head_dim 40 and the uninitialised row padding;
+ * the streamed (32-column chunk) online softmax with lazy rescale of hallo_b200/csrc/attn2_tc.cu (CHUNK = 32) is
+   algebraically the plain softmax.
+These are restatements of the kernels' control flow in numpy, not the kernels themselves; the GPU parity tests
+remain the gate."""
+import numpy as np
+import pytest
+
+
+# ------------------------------------------------------------------------------------------------ PTX fragment model
+def _ldsm(smem, addrs, n, trans=False):
+    """ldmatrix.m8n8.x{n}[.trans].b16: matrix i takes its 8 row addresses from lanes 8i..8i+7."""
+    regs = [[None] * n for _ in range(32)]
+    for i in range(n):
+        M = np.stack([smem[addrs[8 * i + r] // 2: addrs[8 * i + r] // 2 + 8] for r in range(8)])
+        for l in range(32):
+            g, t = l >> 2, l & 3
+            regs[l][i] = (M[g, 2 * t], M[g, 2 * t + 1]) if not trans else (M[2 * t, g], M[2 * t + 1, g])
+    return regs
+
+
+def _mma(d, a, b):
+    """mma.sync.m16n8k16.row.col: d (16x8, C layout) += A (16x16) B (16x8) from per-lane fragments."""
+    A = np.zeros((16, 16))
+    B = np.zeros((16, 8))
+    for l in range(32):
+        g, t = l >> 2, l & 3
+        A[g, 2 * t], A[g, 2 * t + 1] = a[l][0]
+        A[g + 8, 2 * t], A[g + 8, 2 * t + 1] = a[l][1]
+        A[g, 2 * t + 8], A[g, 2 * t + 9] = a[l][2]
+        A[g + 8, 2 * t + 8], A[g + 8, 2 * t + 9] = a[l][3]
+        B[2 * t, g], B[2 * t + 1, g] = b[l][0]
+        B[2 * t + 8, g], B[2 * t + 9, g] = b[l][1]
+    Cm = A @ B
+    for l in range(32):
+        g, t = l >> 2, l & 3
+        d[l][0] += Cm[g, 2 * t]
+        d[l][1] += Cm[g, 2 * t + 1]
+        d[l][2] += Cm[g + 8, 2 * t]
+        d[l][3] += Cm[g + 8, 2 * t + 1]
+
+
+def _tattn_mma_model(D, Fq, Fk, heads, pix, seed=0):
+    rng = np.random.default_rng(seed)
+    MT = 1 if Fq <= 16 else 2
+    NT = 1 if Fk <= 8 else (3 if Fk <= 24 else 4)
+    KS, half_step, KK, NJ = (D + 15) // 16, (D % 16) == 8, (NT + 1) // 2, D // 8
+    C = heads * D
+    ps = C * 2 + 16
+    fs = pix * ps
+    if ((fs >> 4) & 1) == 0:
+        fs += 16
+    smem = np.full((Fq + 2 * Fk) * fs // 2 + 64, np.nan)          # NaN = never-written padding
+    sQ, sK, sV = 0, Fq * fs, (Fq + Fk) * fs
+    Q, K, V = (rng.standard_normal((F, pix, C)) for F in (Fq, Fk, Fk))
+    for base, X in ((sQ, Q), (sK, K), (sV, V)):
+        for f in range(X.shape[0]):
+            for p in range(pix):
+                a = (base + f * fs + p * ps) // 2
+                smem[a:a + C] = X[f, p]
+    scale = 1.0 / np.sqrt(D)
+    worst = 0.0
+    for task in range(pix * heads):
+        p, h = task // heads, task % heads
+        toff = p * ps + h * D * 2
+        s = [[[[0.0] * 4 for _ in range(32)] for _ in range(NT)] for _ in range(MT)]
+        for ks in range(KS):
+            a = []
+            for mt in range(MT):
+                r = _ldsm(smem, [sQ + toff + min(mt * 16 + (l & 7) + ((l >> 3) & 1) * 8, Fq - 1) * fs +
+                                 (2 * ks + (l >> 4)) * 16 for l in range(32)], 4)
+                if half_step and ks == KS - 1:
+                    for l in range(32):
+                        r[l][2] = r[l][3] = (0.0, 0.0)
+                a.append(r)
+            for nt in range(NT):
+                bk = _ldsm(smem, [sK + toff + min(nt * 8 + (l & 7), Fk - 1) * fs + (2 * ks + ((l >> 3) & 1)) * 16
+                                  for l in range(32)], 2)
+                if half_step and ks == KS - 1:
+                    for l in range(32):
+                        bk[l][1] = (0.0, 0.0)
+                for mt in range(MT):
+                    _mma(s[mt][nt], a[mt], bk)
+        inv = [[[0.0, 0.0] for _ in range(32)] for _ in range(MT)]
+        for mt in range(MT):
+            for hh in range(2):
+                mx = [-np.inf] * 32
+                for l in range(32):
+                    for nt in range(NT):
+                        for e in range(2):
+                            if nt * 8 + 2 * (l & 3) + e >= Fk:
+                                s[mt][nt][l][hh * 2 + e] = -np.inf
+                            mx[l] = max(mx[l], s[mt][nt][l][hh * 2 + e])
+                mx = [max(mx[l], mx[l ^ 1]) for l in range(32)]
+                mx = [max(mx[l], mx[l ^ 2]) for l in range(32)]
+                sm = [0.0] * 32
+                for l in range(32):
+                    for nt in range(NT):
+                        for e in range(2):
+                            pe = np.exp((s[mt][nt][l][hh * 2 + e] - mx[l]) * scale)
+                            s[mt][nt][l][hh * 2 + e] = pe
+                            sm[l] += pe
+                sm = [sm[l] + sm[l ^ 1] for l in range(32)]
+                sm = [sm[l] + sm[l ^ 2] for l in range(32)]
+                for l in range(32):
+                    inv[mt][l][hh] = 1.0 / sm[l]
+        pa = [[[[None] * 4 for _ in range(32)] for _ in range(KK)] for _ in range(MT)]
+        for mt in range(MT):
+            for kk in range(KK):
+                for l in range(32):
+                    pa[mt][kk][l][0] = (s[mt][2 * kk][l][0], s[mt][2 * kk][l][1])
+                    pa[mt][kk][l][1] = (s[mt][2 * kk][l][2], s[mt][2 * kk][l][3])
+                    if 2 * kk + 1 < NT:
+                        pa[mt][kk][l][2] = (s[mt][2 * kk + 1][l][0], s[mt][2 * kk + 1][l][1])
+                        pa[mt][kk][l][3] = (s[mt][2 * kk + 1][l][2], s[mt][2 * kk + 1][l][3])
+                    else:
+                        pa[mt][kk][l][2] = pa[mt][kk][l][3] = (0.0, 0.0)
+        out = np.full((Fq, D), np.nan)
+        for j in range(NJ):
+            o = [[[0.0] * 4 for _ in range(32)] for _ in range(MT)]
+            for kk in range(KK):
+                bv = _ldsm(smem, [sV + toff + min(kk * 16 + (l & 15), Fk - 1) * fs + j * 16 for l in range(32)], 2, trans=True)
+                for mt in range(MT):
+                    _mma(o[mt], pa[mt][kk], bv)
+            for mt in range(MT):
+                for hh in range(2):
+                    for l in range(32):
+                        g, t = l >> 2, l & 3
+                        frame = mt * 16 + g + hh * 8
+                        if frame < Fq:
+                            out[frame, 8 * j + 2 * t] = o[mt][l][hh * 2] * inv[mt][l][hh]
+                            out[frame, 8 * j + 2 * t + 1] = o[mt][l][hh * 2 + 1] * inv[mt][l][hh]
+        q, k, v = (X[:, p, h * D:(h + 1) * D] for X in (Q, K, V))
+        sc = q @ k.T * scale
+        pr = np.exp(sc - sc.max(1, keepdims=True))
+        ref = (pr / pr.sum(1, keepdims=True)) @ v
+        assert not np.isnan(out).any()
+        worst = max(worst, float(np.abs(out - ref).max()))
+    return worst
+
+
+@pytest.mark.parametrize("D,Fq,Fk,heads,pix", [(40, 18, 18, 8, 2), (80, 18, 18, 2, 1), (160, 18, 18, 2, 1), (40, 6, 18, 4, 2),
+                                               (40, 3, 3, 8, 3), (40, 32, 32, 2, 1), (80, 17, 25, 2, 1)])
+def test_tattn_mma_fragment_logic(D, Fq, Fk, heads, pix):
+    assert _tattn_mma_model(D, Fq, Fk, heads, pix) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ streamed softmax
+def _streamed_attention_row(srows, v, scale_log2, L, BN=128, threshold=8.0):
+    """One query row of attn2_tc_kernel<CHUNK=32>: K tiles of BN keys, each consumed in 32-column chunks; running
+    reference max m_ref raised only when a chunk maximum exceeds it by > threshold (log2 units)."""
+    m_ref, l_sum = -np.inf, 0.0
+    o = np.zeros(v.shape[1])
+    ntiles = (L + BN - 1) // BN
+    for j in range(ntiles):
+        key0 = j * BN
+        s = np.full(BN, 1e30)                                   # out-of-range columns hold garbage
+        n_valid = min(BN, L - key0)
+        s[:n_valid] = srows[key0:key0 + n_valid]
+        tail = key0 + BN > L
+        pk = np.zeros(BN)
+        ps = 0.0
+        for c in range(BN // 32):
+            sc = s[c * 32:(c + 1) * 32]
+            if not tail:
+                mx = sc.max()
+            else:
+                valid = [sc[i] for i in range(32) if key0 + c * 32 + i < L]
+                mx = max(valid) if valid else -np.inf
+            mx *= scale_log2
+            if mx > m_ref + threshold:
+                m_new = max(m_ref, mx)
+                if j > 0 or c > 0:
+                    f = 2.0 ** (m_ref - m_new)
+                    if j > 0:
+                        o *= f
+                    l_sum *= f
+                    ps *= f
+                    pk[:c * 32] *= f
+                m_ref = m_new
+            e = 2.0 ** (sc * scale_log2 - m_ref)
+            if tail:
+                e = np.where(key0 + c * 32 + np.arange(32) >= L, 0.0, e)
+            ps += e.sum()
+            pk[c * 32:(c + 1) * 32] = e
+        l_sum += ps
+        vv = np.zeros((BN, v.shape[1]))
+        vv[:n_valid] = v[key0:key0 + n_valid]                    # TMA zero-fills rows past L
+        o += pk @ vv
+    return o / l_sum
+
+
+@pytest.mark.parametrize("L,spread", [(256, 1.0), (300, 30.0), (1000, 200.0), (128, 0.01)])
+def test_streamed_softmax_with_lazy_rescale_is_softmax(L, spread):
+    rng = np.random.default_rng(L)
+    d = 40
+    s = rng.standard_normal(L) * spread
+    s[rng.integers(0, L, 5)] += 3 * spread                       # late large scores force rescales mid-tile
+    v = rng.standard_normal((L, d))
+    scale_log2 = 1.4426950408889634 / np.sqrt(d)
+    got = _streamed_attention_row(s, v, scale_log2, L)
+    w = np.exp((s - s.max()) / np.sqrt(d))
+    ref = (w / w.sum()) @ v
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
