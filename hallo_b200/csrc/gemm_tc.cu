@@ -828,6 +828,19 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
     if (p->N % 192 == 0) return launch_gemm<T, 192, 6, 2, true>(p, s);
     if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
   }
+  // option gemm_fill (opt-in, untested on hardware): when the widest N tile leaves SM pairs idle (small M: the
+  // per-rank shapes of a sharded window, levels 2-3), trade shared-memory efficiency for occupancy with BN 128 / 64
+  if (option(OPT_GEMM_FILL) != 0) {
+    const long long rows = p->conv3x3 ? (long long)p->img_n * p->img_h * p->img_w : (long long)p->M;
+    const long long tiles_m2 = ((rows + kBM - 1) / kBM + 1) / 2;
+    const int pairs = num_sms() / 2;
+    const int wide = p->N % 256 == 0 ? 256 : (p->N % 192 == 0 ? 192 : 160);
+    if (tiles_m2 * ((p->N + wide - 1) / wide) < pairs) {
+      if (p->N % 128 == 0 && tiles_m2 * (p->N / 128) >= pairs) return launch_gemm<T, 128, 8, 2>(p, s);
+      if (p->N % 64 == 0) return launch_gemm<T, 64, 8, 2>(p, s);
+      if (p->N % 128 == 0) return launch_gemm<T, 128, 8, 2>(p, s);
+    }
+  }
   // widest N tile that divides N: fewer shared-memory bytes per MMA flop (see the header comment)
   if (p->N % 256 == 0) return launch_gemm<T, 256, 6, 2>(p, s);
   if (p->N % 192 == 0) return launch_gemm<T, 192, 7, 2>(p, s);

@@ -55,7 +55,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU            (default 0)
  *   "attn_v1"     1: force the first-generation attention kernel                                   (default 0)
  *   "xattn_tc"    1: tcgen05 cross-attention instead of the CUDA-core kernel                       (default 0)
- *   "tattn_mma"   1: temporal attention on warp-level tensor-core MMAs instead of CUDA cores      (default 0) */
+ *   "tattn_mma"   1: temporal attention on warp-level tensor-core MMAs instead of CUDA cores      (default 0)
+ *   "gemm_fill"   1: narrower GEMM N tiles (128 / 64) when the widest tile would leave SMs idle    (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 

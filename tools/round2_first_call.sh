@@ -11,7 +11,8 @@ timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baselin
 ALL="HALLO_B200_GEMM_TEPI=1 HALLO_B200_ATTN_CHUNK=1 HALLO_B200_XATTN_TC=1 HALLO_B200_TATTN_MMA=1"
 env $ALL timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline > gpurun_out/r2_bench_all_switches.json 2> gpurun_out/r2_bench_all_switches_ops.log
 timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_bench_shard8.json 2> gpurun_out/r2_bench_shard8_ops.log
-for f in gpurun_out/r2_bench_default.json gpurun_out/r2_bench_all_switches.json gpurun_out/r2_bench_shard8.json; do
+env $ALL HALLO_B200_GEMM_FILL=1 timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_bench_shard8_all_switches.json 2> gpurun_out/r2_bench_shard8_all_switches_ops.log
+for f in gpurun_out/r2_bench_default.json gpurun_out/r2_bench_all_switches.json gpurun_out/r2_bench_shard8.json gpurun_out/r2_bench_shard8_all_switches.json; do
   python - "$f" <<'PY' >> gpurun_out/r2_first_call_summary.txt
 import json, sys
 try:
