@@ -196,7 +196,7 @@ def main():
         from hallo_b200.dist import shard_layout
         from hallo_b200.engine import Shard
         halves, frames_ = shard_layout(args.emulate_shard, args.frames)[args.emulate_shard // 2]   # first cond-half rank
-        shard = Shard(halves=halves, frames=frames_)
+        shard = Shard(halves=halves, frames=frames_, emulate_group=max(1, args.emulate_shard // 2))
         config["emulated_rank_of"] = args.emulate_shard
     eng = DenoiseEngine(W, args.size, args.size, args.frames, shard)
     sch = DDIMScheduler()

@@ -40,6 +40,8 @@ class Shard:
     world: Optional[object] = None          # group for the CFG-combine exchange
     world_size: int = 1
     rank_in_group: int = 0
+    emulate_group: int = 1                  # profiling aid (bench.py --emulate-shard): pretend this many ranks share
+                                            # the CFG half; the temporal K/V of the peers are copies of the local ones
 
 
 class PackedWeights:
@@ -440,6 +442,19 @@ class DenoiseEngine:
         sh = self.shard
         nb, nm, fl = self.nb, self.nm, self.fl
         Fl = nm + fl
+        if sh.group_size == 1 and sh.emulate_group > 1:
+            # single-GPU stand-in for a rank of a sharded job: same buffers, same temporal-attention shape (Fk keys),
+            # device-local copies instead of the NCCL all-gather
+            assert nb == 1
+            g = sh.emulate_group
+            Fk = nm + fl * g
+            src = qkv.view(Fl, L, 3 * C)
+            full = self.buf("mm.kvfull", Fk * L, 2 * C)
+            fv = full.view(Fk, L, 2 * C)
+            fv[:nm].copy_(src[:nm, :, C:])
+            for r in range(g):
+                fv[nm + r * fl: nm + (r + 1) * fl].copy_(src[nm:, :, C:])
+            return full[:, :C], full[:, C:], Fk
         if sh.group_size == 1:
             return qkv[:, C:2 * C], qkv[:, 2 * C:], Fl
         import torch.distributed as dist
