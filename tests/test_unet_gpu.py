@@ -113,3 +113,22 @@ def test_unet_forward_bf16(model):
     finally:
         m.load_state_dict(sd, strict=True)          # restore exact fp16 weights for the other tests
         m.to(dtype=torch.float16)
+
+
+@pytest.mark.xfail(reason="added after the round-1 GPU budget was spent: ragged token counts (L = 2304, 576, 144, 36 -- the "
+                          "level sizes of the 768x768 config) have only been covered per kernel so far", strict=False)
+def test_unet_forward_matches_oracle_port_48x48_ragged(model):
+    """Latent 48x48 / f=2: L is not a multiple of the 256-row attention tile pair (576 = 2.25 x 256, 144, 36), conv
+    boxes overhang (24x24, 12x12, 6x6 images), temporal length 4."""
+    from hallo_b200.spec import UNetConfig
+    from hallo_b200.synth import synth_inputs
+    from oracle import port
+    m, sd = model
+    dev = _dev()
+    cfg = UNetConfig()
+    inp = synth_inputs(cfg, 48, 48, 2, seed=91, timestep=321, motion_scale=(0.9, 1.1, 1.0))
+    ref = port.unet_forward(sd, cfg, inp)
+    out = _run(m, inp, dev)
+    err = rel_l2(out, ref)
+    print(f"48x48 f2: rel L2 vs oracle fp32 = {err:.3e}")
+    assert err < TOL
