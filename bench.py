@@ -199,6 +199,9 @@ def main():
         shard = Shard(halves=halves, frames=frames_, emulate_group=max(1, args.emulate_shard // 2))
         config["emulated_rank_of"] = args.emulate_shard
     eng = DenoiseEngine(W, args.size, args.size, args.frames, shard)
+    if world > 2:
+        config["temporal_exchange"] = ("all-to-all frame<->pixel around each motion module" if eng.motion_a2a
+                                       else "NCCL all-gather of the temporal K/V")
     sch = DDIMScheduler()
     sch.set_timesteps(N_DDIM)
 

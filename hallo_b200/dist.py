@@ -54,3 +54,26 @@ def gather_temporal_kv(local_kv, motion_kv, group, group_size: int):
     full[:nm].copy_(motion_kv)
     dist.all_gather_into_tensor(full[nm:].reshape(-1), local_kv.contiguous().reshape(-1), group=group)
     return full
+
+
+def frames_to_pixels(gn_local, send_buf, out_rows, fl: int, group_size: int, group):
+    """[fl, L, C] rows of this rank's frames -> out_rows [G*fl, L/G, C]: the pixel slice `rank_in_group` of ALL frames of
+    the CFG group in global frame order (all-to-all; chunk r of the result comes from rank r)."""
+    import torch.distributed as dist
+    C = gn_local.shape[-1]
+    Lg = gn_local.numel() // (fl * group_size * C)
+    send_buf.view(group_size, fl, Lg, C).copy_(gn_local.view(fl, group_size, Lg, C).permute(1, 0, 2, 3))
+    dist.all_to_all_single(out_rows, send_buf, group=group)
+    return out_rows
+
+
+def pixels_to_frames(y, recv_buf, residual, out, fl: int, group_size: int, group):
+    """y [G*fl, L/G, C] (all frames, my pixel slice) -> out [fl, L, C] (my frames, all pixels) + residual."""
+    import torch
+    import torch.distributed as dist
+    C = y.shape[-1]
+    Lg = y.numel() // (fl * group_size * C)
+    dist.all_to_all_single(recv_buf, y, group=group)             # chunk g = my frames at pixel slice g
+    torch.add(recv_buf.view(group_size, fl, Lg, C).permute(1, 0, 2, 3), residual.view(fl, group_size, Lg, C),
+              out=out.view(fl, group_size, Lg, C))
+    return out

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -212,6 +213,9 @@ class DenoiseEngine:
         self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
         self.model_out: Optional[torch.Tensor] = None
         self.sample: Optional[torch.Tensor] = None      # per-half fp32 sample for the plain forward() API path
+        # opt-in (HALLO_B200_MOTION_A2A=1, sharded runs): frame<->pixel all-to-all around each motion module instead of
+        # the temporal K/V all-gather; untested on hardware in round 1
+        self.motion_a2a = (os.environ.get("HALLO_B200_MOTION_A2A", "0") not in ("", "0")) and self.shard.group_size > 1
 
     # ------------------------------------------------------------------ buffers
     def buf(self, tag: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
@@ -264,6 +268,7 @@ class DenoiseEngine:
         self._wset("ref_index", torch.tensor(ridx, dtype=torch.int32, device=dev))
         # temporal positions: motion frames 0..nm-1, then nm + global frame id
         self._wset("pe_index", torch.tensor(list(range(nm)) + [nm + g for g in frames], dtype=torch.int32, device=dev))
+        self._wset("pe_index_all", torch.arange(nm + f, dtype=torch.int32, device=dev))     # pixel-sharded motion path
 
         ehs = encoder_hidden_states.to(dev, dt)[halves]                       # [nb, 4, 768]
         aud = audio_embedding.to(dev, dt)[halves][:, fr_idx]                  # [nb, fl, 32, 768]
@@ -466,7 +471,57 @@ class DenoiseEngine:
         dist.all_gather_into_tensor(full.view(Fk, L, 2 * C)[nm:].reshape(-1), loc.reshape(-1), group=sh.group)
         return full[:, :C], full[:, C:], Fk
 
+    def _motion_a2a(self, name: str, x, level: int, C: int, out_tag: str):
+        """Motion module with frame<->pixel ownership swapped around it (SURVEY.md 8e "alternative"): every rank of the
+        CFG group normalises its own frames (GroupNorm needs whole frames), an all-to-all hands each rank the pixel slice
+        [me*L/G, (me+1)*L/G) of ALL frames, the module (proj_in .. proj_out, temporal attention over the nm + f frames)
+        runs on that slice with no replicated motion-frame work and no K/V exchange, and a second all-to-all returns the
+        rows to their frame owners, which add the residual.  Exchanged bytes: 2 * (G-1)/G * fl*L*C*2 per module instead
+        of 2 * (G-1) * fl*L*2C*2 for the two K/V all-gathers."""
+        W, win, H, sh = self.W, self.window, self.cfg.heads, self.shard
+        nm, fl, gs, me = self.nm, self.fl, sh.group_size, sh.rank_in_group
+        assert self.nb == 1
+        L = self.L(level)
+        assert L % gs == 0, "pixel-sharded motion path needs L divisible by the group size"
+        Lg, F = L // gs, fl * gs
+        F18 = nm + F
+        M18 = F18 * Lg
+        tt = f"{name}.temporal_transformer"
+        tb = f"{tt}.transformer_blocks.0"
+        # GroupNorm of the local frames (frame-major rows), then scatter pixel slices to their owners
+        gnl = self.buf("mm.gnl", fl * L, C)
+        self._gn(x, f"{tt}.norm", gnl, fl, L, 1e-6, False)
+        from .dist import frames_to_pixels, pixels_to_frames
+        send = self.buf("mm.a2a.s", gs * fl * Lg, C)
+        x18 = self.buf("mm.x18", M18, C)
+        gn18 = self.buf(f"{name}.gn18", (nm + fl) * L, C)              # rows of frames [0, nm): begin_window
+        x18.view(F18, Lg, C)[:nm].copy_(gn18.view(nm + fl, L, C)[:nm, me * Lg:(me + 1) * Lg])
+        frames_to_pixels(gnl, send, x18[nm * Lg:], fl, gs, sh.group)   # chunk r = frames of rank r, my pixels
+        h = self.buf("mm.h", M18, C)
+        ops.gemm(x18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"])
+        for a in range(2):
+            n = self._ln(h, f"{tb}.norms.{a}", "mm.ln", pe=W[f"{tb}.attention_blocks.{a}.pe"],
+                         pe_index=win["pe_index_all"], tokens_per_frame=Lg, frames=F18)
+            qkv = self.buf("mm.qkv", M18, 3 * C)
+            ops.gemm(n, W[f"{tb}.attention_blocks.{a}.qkv"], qkv)
+            o = self.buf("mm.attn", M18, C)
+            ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, batch=1, fq=F18, fk=F18, tokens=Lg,
+                                   heads=H)
+            h2 = self.buf(f"mm.h{a + 1}", M18, C)
+            ops.gemm(o, W[f"{tb}.attention_blocks.{a}.to_out.0.w"], h2,
+                     bias=W[f"{tb}.attention_blocks.{a}.to_out.0.b"], residual=h)
+            h = h2
+        h = self._ff(h, f"{tb}.ff", f"{tb}.ff_norm", "mm.h3")
+        y = self.buf("mm.y", F * Lg, C)                                # real frames only, global frame order
+        ops.gemm(h[nm * Lg:], W[f"{tt}.proj_out.w"], y, bias=W[f"{tt}.proj_out.b"])
+        recv = self.buf("mm.a2a.r", gs * fl * Lg, C)
+        out = self.buf(out_tag, fl * L, C)
+        pixels_to_frames(y, recv, x, out, fl, gs, sh.group)            # chunk g = my frames, pixel slice g; + residual
+        return out
+
     def _motion(self, name: str, attn_name: str, x, level: int, C: int, out_tag: str):
+        if self.motion_a2a:
+            return self._motion_a2a(name, x, level, C, out_tag)
         W, win, H = self.W, self.window, self.cfg.heads
         nb, nm, fl = self.nb, self.nm, self.fl
         Fl = nm + fl

@@ -113,7 +113,7 @@ def test_shard_layout():
 WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["HB_ROOT"])
-from hallo_b200.dist import plan_shard, gather_temporal_kv
+from hallo_b200.dist import plan_shard, gather_temporal_kv, frames_to_pixels, pixels_to_frames
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 n_frames, nm, L, C2 = 8, 2, 3, 4
@@ -132,6 +132,23 @@ mo = torch.full((5, 8), float(rank))
 allm = torch.empty(world * 5, 8)
 dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1))
 assert float(allm[:5].mean()) == 0.0 and float(allm[5:].mean()) == 1.0
+# frame<->pixel exchange around a motion module (engine._motion_a2a): a per-pixel op that mixes ALL frames (here a
+# cumulative sum over the frame axis + a per-frame scale) computed on pixel slices must equal the unsharded result
+Lp, Cc = 6, 4
+xg = torch.arange(n_frames * Lp * Cc, dtype=torch.float32).reshape(n_frames, Lp, Cc) / 7.0      # all frames (global)
+x_loc = xg[rank * fl:(rank + 1) * fl].contiguous()                                               # my frames
+Lg = Lp // 2
+send = torch.empty(2 * fl * Lg, Cc)
+allf = torch.empty(2 * fl * Lg, Cc)
+frames_to_pixels(x_loc.reshape(fl * Lp, Cc), send, allf, fl, 2, g)
+assert torch.equal(allf.view(n_frames, Lg, Cc), xg[:, rank * Lg:(rank + 1) * Lg]), rank     # my pixel slice of all frames
+scale = torch.arange(1, n_frames + 1, dtype=torch.float32).view(n_frames, 1, 1)
+y = (allf.view(n_frames, Lg, Cc).cumsum(0) * scale).reshape(n_frames * Lg, Cc).contiguous()
+recv = torch.empty_like(y)
+out = torch.empty(fl * Lp, Cc)
+pixels_to_frames(y, recv, x_loc.reshape(fl * Lp, Cc), out, fl, 2, g)
+ref = (xg.cumsum(0) * scale + xg)[rank * fl:(rank + 1) * fl]
+assert torch.allclose(out.view(fl, Lp, Cc), ref), rank
 dist.destroy_process_group()
 print("ok", rank)
 '''
