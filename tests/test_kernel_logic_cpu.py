@@ -205,3 +205,54 @@ def test_streamed_softmax_with_lazy_rescale_is_softmax(L, spread):
     w = np.exp((s - s.max()) / np.sqrt(d))
     ref = (w / w.sum()) @ v
     assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------------ TMA-store epilogue
+def _tepi_cover(BN, geglu):
+    """Panel / unit assignment of gemm_tc_kernel<TEPI> (hallo_b200/csrc/gemm_tc.cu): returns, per output column of a
+    tile, how many times it is written, and per accumulator column how many times it is read."""
+    out_bn = BN // 2 if geglu else BN
+    panels = BN // 64 if geglu else BN // 32
+    written = np.zeros(out_bn, int)
+    read = np.zeros(BN, int)
+    max_units = 2 * ((BN // 64 + 1) // 2) if BN % 64 == 0 else (BN // 32 + 1) // 2
+    for grp in (0, 1):
+        my_panels = (panels - grp + 1) // 2
+        my_units = 2 * my_panels if geglu else my_panels
+        assert my_units <= max_units
+        for u in range(my_units):
+            col = (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 if geglu else (grp + 2 * u) * 32
+            read[col:col + 32] += 1
+            if geglu:
+                panel, chunks = grp + 2 * (u >> 1), [(u & 1) * 2, (u & 1) * 2 + 1]
+            else:
+                panel, chunks = grp + 2 * u, [0, 1, 2, 3]
+            for c in chunks:
+                written[panel * 32 + c * 8: panel * 32 + c * 8 + 8] += 1
+            # value/gate pairing of the GEGLU weight packing: accumulator column 2j, 2j+1 -> output column j
+            if geglu:
+                assert (col >> 1) == panel * 32 + chunks[0] * 8
+    return written, read
+
+
+@pytest.mark.parametrize("BN,geglu", [(256, False), (192, False), (160, False), (128, False), (256, True), (192, True)])
+def test_tepi_panel_assignment_covers_each_column_once(BN, geglu):
+    written, read = _tepi_cover(BN, geglu)
+    assert (written == 1).all() and (read == 1).all()
+
+
+def test_tepi_swizzle64_is_bank_conflict_free_and_bijective():
+    """Panel buffer: 128 rows x 64 B, chunk c of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4) (CU_TENSOR_MAP_SWIZZLE_64B:
+    address bits [4:5] ^= bits [7:8]).  A 128-bit shared access is served per quarter-warp: the 8 lanes (= 8 consecutive
+    rows, same logical chunk) must touch 8 different 16-byte bank groups."""
+    seen = set()
+    for r in range(128):
+        for c in range(4):
+            off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4)
+            assert off == (r * 64 + c * 16) ^ ((((r * 64 + c * 16) >> 7) & 3) << 4)     # the hardware's address form
+            seen.add(off)
+    assert len(seen) == 512 and max(seen) < 8192
+    for r0 in range(0, 128, 8):
+        for c in range(4):
+            groups = {((r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) % 128) // 16 for r in range(r0, r0 + 8)}
+            assert len(groups) == 8
