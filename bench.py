@@ -310,6 +310,18 @@ def main():
     h2d = lat_host.numel() * 4 + window_bytes() // N_DDIM
     d2h = lat_back.numel() * 4
 
+    # ---------------- optional per-op table: one eager step on EVERY rank (the collectives need all of them) ----------------
+    prof_saved = None
+    if args.profile_ops:
+        ops.PROFILE = []
+        eng.graph_saved, eng.graph = eng.graph, None
+        eng.step()
+        torch.cuda.synchronize()
+        prof_saved = [(name, a.elapsed_time(b_)) for name, a, b_ in ops.PROFILE]
+        ops.PROFILE = None
+        eng.graph = eng.graph_saved
+        barrier()
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -357,30 +369,21 @@ def main():
                                "peak": peaks["sustained"], "frac": fl["total"] / (ms_step * 1e-3) / 1e12 / world / peaks["sustained"],
                                "unit": "TFLOP/s per GPU (48.44 TFLOP algorithmic per forward)"}}
 
-    if args.profile_ops:
-        ops.PROFILE = []
-        eng.graph_saved, eng.graph = eng.graph, None
-        eng.step()
-        torch.cuda.synchronize()
-        agg = {}
-        for name, a, b_ in ops.PROFILE:
+    if prof_saved is not None:
+        agg, byname = {}, {}
+        for name, ms_ in prof_saved:
             kind = name.split(" ")[0]
             agg.setdefault(kind, [0.0, 0])
-            agg[kind][0] += a.elapsed_time(b_)
+            agg[kind][0] += ms_
             agg[kind][1] += 1
-        prof_saved = ops.PROFILE
-        ops.PROFILE = None
-        eng.graph = eng.graph_saved
-        byname = {}
-        for name, a, b_ in prof_saved:
             byname.setdefault(name, [0.0, 0])
-            byname[name][0] += a.elapsed_time(b_)
+            byname[name][0] += ms_
             byname[name][1] += 1
         tot = sum(v[0] for v in agg.values())
         print("# top shapes (eager, includes ~10 us launch gap each):", file=sys.stderr)
-        for k, v in sorted(byname.items(), key=lambda kv: -kv[1][0])[:28]:
+        for k, v in sorted(byname.items(), key=lambda kv: -kv[1][0])[:32]:
             print(f"#     {k:44s} {v[0]:8.3f} ms x{v[1]:3d}  {1e3 * v[0] / v[1]:8.1f} us each", file=sys.stderr)
-        print(f"# per-op breakdown of one eager step ({tot:.2f} ms summed)", file=sys.stderr)
+        print(f"# per-op breakdown of one eager step on rank 0 ({tot:.2f} ms summed)", file=sys.stderr)
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"#   {k:22s} {v[0]:9.3f} ms  {100 * v[0] / tot:5.1f} %  x{v[1]}", file=sys.stderr)
 

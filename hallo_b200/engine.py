@@ -465,10 +465,12 @@ class DenoiseEngine:
         import torch.distributed as dist
         assert nb == 1
         Fk = nm + fl * sh.group_size
-        loc = qkv.view(Fl, L, 3 * C)[nm:, :, C:].contiguous()                     # [fl, L, 2C]
-        full = self.buf("mm.kvfull", Fk * L, 2 * C)
-        full.view(Fk, L, 2 * C)[:nm].copy_(qkv.view(Fl, L, 3 * C)[:nm, :, C:])
-        dist.all_gather_into_tensor(full.view(Fk, L, 2 * C)[nm:].reshape(-1), loc.reshape(-1), group=sh.group)
+        with ops.timed_region(f"kv_allgather_pack C{C} L{L}"):
+            loc = qkv.view(Fl, L, 3 * C)[nm:, :, C:].contiguous()                 # [fl, L, 2C]
+            full = self.buf("mm.kvfull", Fk * L, 2 * C)
+            full.view(Fk, L, 2 * C)[:nm].copy_(qkv.view(Fl, L, 3 * C)[:nm, :, C:])
+        with ops.timed_region(f"kv_allgather_nccl C{C} L{L} G{sh.group_size}"):
+            dist.all_gather_into_tensor(full.view(Fk, L, 2 * C)[nm:].reshape(-1), loc.reshape(-1), group=sh.group)
         return full[:, :C], full[:, C:], Fk
 
     def _motion_a2a(self, name: str, x, level: int, C: int, out_tag: str):
@@ -496,7 +498,8 @@ class DenoiseEngine:
         x18 = self.buf("mm.x18", M18, C)
         gn18 = self.buf(f"{name}.gn18", (nm + fl) * L, C)              # rows of frames [0, nm): begin_window
         x18.view(F18, Lg, C)[:nm].copy_(gn18.view(nm + fl, L, C)[:nm, me * Lg:(me + 1) * Lg])
-        frames_to_pixels(gnl, send, x18[nm * Lg:], fl, gs, sh.group)   # chunk r = frames of rank r, my pixels
+        with ops.timed_region(f"a2a_frames_to_pixels C{C} L{L} G{gs}"):
+            frames_to_pixels(gnl, send, x18[nm * Lg:], fl, gs, sh.group)   # chunk r = frames of rank r, my pixels
         h = self.buf("mm.h", M18, C)
         ops.gemm(x18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"])
         for a in range(2):
@@ -516,7 +519,8 @@ class DenoiseEngine:
         ops.gemm(h[nm * Lg:], W[f"{tt}.proj_out.w"], y, bias=W[f"{tt}.proj_out.b"])
         recv = self.buf("mm.a2a.r", gs * fl * Lg, C)
         out = self.buf(out_tag, fl * L, C)
-        pixels_to_frames(y, recv, x, out, fl, gs, sh.group)            # chunk g = my frames, pixel slice g; + residual
+        with ops.timed_region(f"a2a_pixels_to_frames C{C} L{L} G{gs}"):
+            pixels_to_frames(y, recv, x, out, fl, gs, sh.group)        # chunk g = my frames, pixel slice g; + residual
         return out
 
     def _motion(self, name: str, attn_name: str, x, level: int, C: int, out_tag: str):
@@ -651,7 +655,8 @@ class DenoiseEngine:
             # the two CFG halves live on different ranks: exchange the (tiny) model outputs
             import torch.distributed as dist
             allm = self.buf("out.all", sh.world_size * mo.shape[0], mo.shape[1])
-            dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1), group=sh.world)
+            with ops.timed_region("cfg_exchange_nccl"):
+                dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1), group=sh.world)
             gs = sh.group_size
             me = sh.rank_in_group
             n = mo.shape[0]

@@ -35,6 +35,27 @@ def _timed(name_fn):
     return deco
 
 
+class timed_region:
+    """`with ops.timed_region("name"):` -- same (name, start, end) record as the decorated ops, for engine-level steps
+    such as the NCCL exchanges; free when PROFILE is None."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and hasattr(self, "e0"):
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.e0, e1))
+        return False
+
+
 def _rowmajor_ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and t.stride(1) == 1, f"need row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
     return t.stride(0)

@@ -23,3 +23,12 @@ except Exception as e:
 PY
 done
 cat gpurun_out/r2_first_call_summary.txt
+# Multi-GPU follow-up (separate call, charged N x):
+#   /usr/local/graft/bin/gpurun --gpus 4 --timeout 1200 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 \
+#      --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 10 --warmup 3 --profile-ops \
+#      > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4_ops.log; \
+#    HALLO_B200_MOTION_A2A=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+#      --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --profile-ops \
+#      > gpurun_out/r2_bench_n4_a2a.json 2> gpurun_out/r2_bench_n4_a2a_ops.log'
+# (the per-op table now includes kv_allgather_* / a2a_* / cfg_exchange_nccl rows; parity of the a2a path first:
+#  HALLO_B200_MOTION_A2A=1 torchrun --nproc-per-node 2 tools/debug_gather.py)
