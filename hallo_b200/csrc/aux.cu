@@ -188,6 +188,115 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const T* __r
   }
 }
 
+// One-launch GroupNorm for slabs that fit shared memory: CTA (frame n, group g) reads its [HW x C/G] slab once
+// (kept in shared memory as raw 16-bit pairs), reduces sum / sum-of-squares in the CTA, then normalises (+SiLU) out
+// of shared memory.  x is read once instead of twice and the memset / stats / finalize / apply launches collapse
+// into one; same arithmetic as gn_stats + gn_finalize + gn_apply (fp32 sums, var = E[x^2] - mean^2).
+// Opt-in (option "gn_fused") until tests/test_aux_gpu.py::test_groupnorm* have passed with it on hardware.
+template <int V>
+struct GnVec;                                     // V channel pairs = 4V bytes per access
+template <>
+struct GnVec<1> { using type = uint32_t; };
+template <>
+struct GnVec<2> { using type = uint2; };
+template <>
+struct GnVec<4> { using type = uint4; };
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gn_fused_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
+                                                        int HW, int G, const T* __restrict__ gamma,
+                                                        const T* __restrict__ beta, float eps, int silu,
+                                                        T* __restrict__ out, int fpb_in, int fpb_out, int frame_off) {
+  using Vec = typename GnVec<V>::type;
+  extern __shared__ uint4 gn_slab_raw[];           // [HW][cpg / (2V)] vectors of V channel pairs
+  Vec* slab = reinterpret_cast<Vec*>(gn_slab_raw);
+  __shared__ float red[2][8];
+  __shared__ float stat[2];
+  const int C = C1 + C2;
+  const int cpg = C / G;
+  const int vpp = cpg / (2 * V);                   // vectors per pixel in this group
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int c_base = g * cpg;
+  const int total = HW * vpp;
+  auto src_of = [&](int i) -> const Vec* {
+    const int p = i / vpp;
+    const int c = c_base + 2 * V * (i - p * vpp);
+    const T* src = (c < C1) ? x1 + ((long long)n * HW + p) * C1 + c : x2 + ((long long)n * HW + p) * C2 + (c - C1);
+    return reinterpret_cast<const Vec*>(src);
+  };
+  float s = 0.f, q = 0.f;
+  auto accum = [&](const Vec& u) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float2 v = Cvt<T>::unpack2(w[k]);
+      s += v.x + v.y;
+      q += v.x * v.x + v.y * v.y;
+    }
+  };
+  int i = threadIdx.x;
+  for (; i + 768 < total; i += 1024) {             // 4 independent loads in flight per thread
+    Vec u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *src_of(i + k * 256);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      slab[i + k * 256] = u[k];
+      accum(u[k]);
+    }
+  }
+  for (; i < total; i += 256) {
+    const Vec u = *src_of(i);
+    slab[i] = u;
+    accum(u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    const float cnt = (float)cpg * HW;
+    const float m = a / cnt;
+    const float var = fmaxf(b / cnt - m * m, 0.f);
+    stat[0] = m;
+    stat[1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const float m = stat[0], r = stat[1];
+  const int n_out = (n / fpb_in) * fpb_out + frame_off + (n % fpb_in);
+  for (int j = threadIdx.x; j < total; j += 256) {
+    const int p = j / vpp;
+    const int c = c_base + 2 * V * (j - p * vpp);
+    Vec u = slab[j];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float2 v = Cvt<T>::unpack2(w[k]);
+      const float g0 = Cvt<T>::to_f(gamma[c + 2 * k]) * r, g1 = Cvt<T>::to_f(gamma[c + 2 * k + 1]) * r;
+      float y0 = fmaf(v.x, g0, Cvt<T>::to_f(beta[c + 2 * k]) - m * g0);
+      float y1 = fmaf(v.y, g1, Cvt<T>::to_f(beta[c + 2 * k + 1]) - m * g1);
+      if (silu) {
+        y0 = silu_f(Cvt<T>::to_f(Cvt<T>::from_f(y0)));   // reference rounds the GN output before SiLU
+        y1 = silu_f(Cvt<T>::to_f(Cvt<T>::from_f(y1)));
+      }
+      w[k] = Cvt<T>::pack2(y0, y1);
+    }
+    *reinterpret_cast<Vec*>(out + ((long long)n_out * HW + p) * C + c) = u;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1, int C1,
                                                        const T* __restrict__ x2, int C2, int HW,
@@ -680,6 +789,23 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
   if (C1 % 8 || C2 % 8 || C % G || G > 64 || (C2 > 0 && !x2))
     return fail(HB_ERR_BAD_SHAPE, "groupnorm: C1=%d C2=%d G=%d", C1, C2, G);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // one-launch path for slabs (HW x C/G halfs) that fit shared memory -- opt-in, see gn_fused_kernel
+    const int cpg = C / G;
+    const size_t slab = (size_t)HW * cpg * 2;
+    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024) {
+      if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
+      const int vw = (cpg % 8 == 0) ? 4 : ((cpg % 4 == 0) ? 2 : 1);     // channel pairs per access (16 / 8 / 4 bytes)
+      HB_DISPATCH_T(dtype, {
+        auto kern = vw == 4 ? gn_fused_kernel<T, 4> : (vw == 2 ? gn_fused_kernel<T, 2> : gn_fused_kernel<T, 1>);
+        HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        kern<<<dim3(G, N), 256, slab, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, G, (const T*)gamma, (const T*)beta,
+                                           eps, silu, (T*)out, fpb_in, fpb_out, frame_off);
+      })
+      HB_LAUNCH_CHECK();
+      return HB_OK;
+    }
+  }
   HB_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * G, s));
   float* scsh = stats_ws + 2 * (size_t)N * G;          // workspace tail: [N][2][C] scale / shift
   const int nvec = C / 8;

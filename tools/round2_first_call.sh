@@ -8,7 +8,7 @@ echo "default tests exit $?" | tee gpurun_out/r2_first_call_summary.txt
 bash tools/run_experimental.sh > gpurun_out/r2_experimental.log 2>&1
 cat gpurun_out/exp_summary.txt >> gpurun_out/r2_first_call_summary.txt
 timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default_ops.log
-ALL="HALLO_B200_GEMM_TEPI=1 HALLO_B200_ATTN_CHUNK=1 HALLO_B200_XATTN_TC=1 HALLO_B200_TATTN_MMA=1"
+ALL="HALLO_B200_GEMM_TEPI=1 HALLO_B200_ATTN_CHUNK=1 HALLO_B200_XATTN_TC=1 HALLO_B200_TATTN_MMA=1 HALLO_B200_GN_FUSED=1"
 env $ALL timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline > gpurun_out/r2_bench_all_switches.json 2> gpurun_out/r2_bench_all_switches_ops.log
 timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_bench_shard8.json 2> gpurun_out/r2_bench_shard8_ops.log
 env $ALL HALLO_B200_GEMM_FILL=1 timeout 600 python bench.py --steps 10 --warmup 3 --profile-ops --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_bench_shard8_all_switches.json 2> gpurun_out/r2_bench_shard8_all_switches_ops.log

@@ -13,6 +13,7 @@ run gemm_tepi  HALLO_B200_GEMM_TEPI=1  tests/test_gemm_gpu.py tests/test_aux_gpu
 run attn_chunk HALLO_B200_ATTN_CHUNK=1 tests/test_attention_gpu.py tests/test_unet_gpu.py
 run xattn_tc   HALLO_B200_XATTN_TC=1   tests/test_aux_gpu.py tests/test_unet_gpu.py
 run gemm_fill  HALLO_B200_GEMM_FILL=1  tests/test_gemm_gpu.py tests/test_aux_gpu.py tests/test_unet_gpu.py
+run gn_fused   HALLO_B200_GN_FUSED=1   tests/test_aux_gpu.py tests/test_unet_gpu.py
 run tattn_mma  HALLO_B200_TATTN_MMA=1  tests/test_aux_gpu.py tests/test_unet_gpu.py tests/test_pipeline_gpu.py
 # speed: baseline first, then each switch
 timeout 600 python tools/kbench.py gemm conv attn > gpurun_out/exp_kbench_base.log 2>&1
