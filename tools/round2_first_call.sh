@@ -32,3 +32,4 @@ cat gpurun_out/r2_first_call_summary.txt
 #      > gpurun_out/r2_bench_n4_a2a.json 2> gpurun_out/r2_bench_n4_a2a_ops.log'
 # (the per-op table now includes kv_allgather_* / a2a_* / cfg_exchange_nccl rows; parity of the a2a path first:
 #  HALLO_B200_MOTION_A2A=1 torchrun --nproc-per-node 2 tools/debug_gather.py)
+timeout 300 python tools/ubench.py > gpurun_out/r2_ubench.log 2>&1
