@@ -9,7 +9,8 @@ HALLO_B200_ATTN_CHUNK=1 $NCU -k regex:attn2_tc -o gpurun_out/r2_attn_chunk pytho
 $NCU -k regex:gemm_tc -o gpurun_out/r2_gemm_k320_default python tools/prof_gemm.py > gpurun_out/r2_ncu_gemm_default.log 2>&1
 HALLO_B200_GEMM_TEPI=1 $NCU -k regex:gemm_tc -o gpurun_out/r2_gemm_k320_tepi python tools/prof_gemm.py > gpurun_out/r2_ncu_gemm_tepi.log 2>&1
 GEGLU=1 N=2560 $NCU -k regex:gemm_tc -o gpurun_out/r2_gemm_geglu_default python tools/prof_gemm.py > gpurun_out/r2_ncu_geglu_default.log 2>&1
-for r in gpurun_out/r2_attn_default gpurun_out/r2_attn_chunk gpurun_out/r2_gemm_k320_default gpurun_out/r2_gemm_k320_tepi gpurun_out/r2_gemm_geglu_default; do
+$NCU -k regex:gemm_tc -o gpurun_out/r2_conv_l0_default python tools/prof_conv.py > gpurun_out/r2_ncu_conv_default.log 2>&1
+for r in gpurun_out/r2_conv_l0_default gpurun_out/r2_attn_default gpurun_out/r2_attn_chunk gpurun_out/r2_gemm_k320_default gpurun_out/r2_gemm_k320_tepi gpurun_out/r2_gemm_geglu_default; do
   [ -f $r.ncu-rep ] || continue
   ncu -i $r.ncu-rep --page raw --csv 2>/dev/null | python - "$r" <<'PY'
 import csv, sys
