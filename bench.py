@@ -199,6 +199,12 @@ def main():
         shard = Shard(halves=halves, frames=frames_, emulate_group=max(1, args.emulate_shard // 2))
         config["emulated_rank_of"] = args.emulate_shard
     eng = DenoiseEngine(W, args.size, args.size, args.frames, shard)
+    # record the kernel-selection switches this line was measured with (all 0 = the hardware-validated defaults)
+    try:
+        config["switches"] = {n: lib.get_option(n) for n in ("gemm_tepi", "gemm_1cta", "gemm_fill", "attn_chunk", "attn_poly",
+                                                              "attn_v1", "xattn_tc", "tattn_mma", "gn_fused")}
+    except Exception:
+        pass
     if world > 2:
         config["temporal_exchange"] = ("all-to-all frame<->pixel around each motion module" if eng.motion_a2a
                                        else "NCCL all-gather of the temporal K/V")
