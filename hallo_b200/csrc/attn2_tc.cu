@@ -19,6 +19,8 @@
 //   + 64/128 MUFU.EX2 issued back to back                                   2.96 ms  (BN=128: 3.60 ms)
 // i.e. at head_dim 40 the step is bound by the SFU (16 ex2/clk/SM) plus per-step fixed latencies, and the
 // simplest schedule won; the next lever is moving a share of the exponentials to the FMA pipe.
+#include <type_traits>
+
 #include "host_common.cuh"
 #include "ptx.cuh"
 
@@ -51,7 +53,10 @@ struct Attn2Cfg {
 //             chunk c is exponentiated (online softmax per chunk, lazy rescale).  TMEM reads run at
 //             ~64 B/clk/SM, so the 64 KB S tile costs ~1000 clk -- as much as its 16 K exponentials on the
 //             SFU; serialised (CHUNK 0) the two add up, streamed they overlap.
-template <typename T, int D, int BN, int POLY, int CHUNK = 0>
+// ONES (head_dim 40 only, with CHUNK): the MMA warp writes 1.0 into column 40 of every V row (the columns 40..47 of
+//        the 48-wide PV tile are TMA zero fill), so O[:, 40] accumulates the softmax denominator on the tensor
+//        core -- with the same fp16-rounded P that builds O -- and the 128 FADD per row and step disappear.
+template <typename T, int D, int BN, int POLY, int CHUNK = 0, bool ONES = false>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -187,6 +192,19 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int t = 0; t < 2; ++t) {
         mbar_wait(&p_full[t], j & 1, 0x83);
         if (t == 0) mbar_wait(&v_full[vstage], vphase, 0x84);
+        if (ONES && t == 0) {
+          // column 40 = chunk 5 of the 128-byte row, 128B swizzle: chunk ^= row & 7
+          const uint16_t one = std::is_same<T, __half>::value ? (uint16_t)0x3C00 : (uint16_t)0x3F80;
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) {
+            const uint32_t r = (uint32_t)lane + 32u * i;
+            asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(sV + vstage * CF::kKVBytes + r * 128u + ((5u ^ (r & 7u)) << 4)),
+                         "h"(one)
+                         : "memory");
+          }
+          fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's operand reads
+          __syncwarp();
+        }
         if (more && t == 0) mbar_wait(&k_full[kstage], kphase, 0x85);
         tc_fence_after();
         if (lane == 0) {
@@ -345,9 +363,11 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tmem_st_x8(o_addr + cc * 8, r);
               }
             }
-            l_sum *= f;
+            if (!ONES) {
+              l_sum *= f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ps4[q] *= f;
+              for (int q = 0; q < 4; ++q) ps4[q] *= f;
+            }
 #pragma unroll
             for (int i = 0; i < c * 16; ++i) {           // P of the earlier chunks of this step
               const float2 v = Cvt<T>::unpack2(pk[i]);
@@ -367,7 +387,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (key0 + c * 32 + i >= p.L) e0 = 0.f;
             if (key0 + c * 32 + i + 1 >= p.L) e1 = 0.f;
           }
-          ps4[(i >> 1) & 3] += e0 + e1;
+          if (!ONES) ps4[(i >> 1) & 3] += e0 + e1;
           pk[c * 16 + (i >> 1)] = Cvt<T>::pack2(e0, e1);
         }
       }
@@ -383,7 +403,15 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- epilogue: O / l -> global ----
     mbar_wait(&o_done[t], 0, 0x92);
     tc_fence_after();
-    const float inv = 1.0f / l_sum;
+    float inv;
+    if (ONES) {
+      uint32_t r[8];
+      tmem_ld_x8(o_addr + 40, r);                      // O[:, 40] = sum of the (rounded) probabilities
+      tmem_ld_wait();
+      inv = 1.0f / __uint_as_float(r[0]);
+    } else {
+      inv = 1.0f / l_sum;
+    }
     const int qrow = qt * 256 + t * 128 + row;
     T* out = reinterpret_cast<T*>(p.O) + ((long long)frame * p.L + qrow) * p.ldo + head * D;
 #pragma unroll
@@ -410,7 +438,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <typename T, int D, int BN, int POLY, int CHUNK = 0>
+template <typename T, int D, int BN, int POLY, int CHUNK = 0, bool ONES = false>
 static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   using CF = Attn2Cfg<D, BN>;
   static_assert(CF::kTotal <= 232448, "attention v2 smem budget");
@@ -436,7 +464,8 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   d.O = q->O;
   d.ldo = q->ldo;
   d.scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  auto kern = attn2_tc_kernel<T, D, BN, POLY, CHUNK>;
+  static_assert(!ONES || (D == 40 && CHUNK != 0), "ones column: head_dim 40, streamed softmax");
+  auto kern = attn2_tc_kernel<T, D, BN, POLY, CHUNK, ONES>;
   static bool attr_set = false;
   if (!attr_set) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kTotal));

@@ -10,11 +10,17 @@ static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
   const int poly = option(OPT_ATTN_POLY);
   // streamed softmax (attn2_tc.cu, CHUNK = 32): written after the last GPU session of round 1, so it stays
   // opt-in until tests/test_attention_gpu.py has passed with attn_chunk = 1 on hardware
-  const bool chunk = option(OPT_ATTN_CHUNK) != 0;
+  const int chunk_opt = option(OPT_ATTN_CHUNK);   // 1: streamed softmax, 2: + row sums on the tensor core (d = 40)
+  const bool chunk = chunk_opt != 0;
   switch (p->head_dim) {
     // v2 (two query tiles per CTA, P in TMEM) when a frame has at least one full pair of tiles; the
     // single-tile kernel otherwise (small L) and for head_dim 160 at small L.
     case 40:
+      if (p->L >= 256 && !v1 && chunk_opt == 2) {
+        if (poly == 4) return launch_attn2<T, 40, 128, 4, 32, true>(p, s);
+        if (poly == 3) return launch_attn2<T, 40, 128, 3, 32, true>(p, s);
+        return launch_attn2<T, 40, 128, 0, 32, true>(p, s);
+      }
       if (p->L >= 256 && !v1 && chunk) {
         if (poly == 4) return launch_attn2<T, 40, 128, 4, 32>(p, s);
         if (poly == 3) return launch_attn2<T, 40, 128, 3, 32>(p, s);

@@ -51,7 +51,8 @@ int64_t hallo_b200_launch_count(int reset);
  * case) and can be changed at run time; unknown names return HB_ERR_BAD_SHAPE / -1.
  *   "gemm_tepi"   1: GEMM / conv epilogue staged through shared memory and written by TMA stores  (default 0)
  *   "gemm_1cta"   1: force the single-CTA GEMM kernel                                              (default 0)
- *   "attn_chunk"  1: attention streams S through registers in 32-column chunks                     (default 0)
+ *   "attn_chunk"  1: attention streams S through registers in 32-column chunks; 2: and (head_dim 40)
+ *                    accumulates the softmax row sums on the tensor core via a ones column in V    (default 0)
  *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU            (default 0)
  *   "attn_v1"     1: force the first-generation attention kernel                                   (default 0)
  *   "xattn_tc"    1: tcgen05 cross-attention instead of the CUDA-core kernel                       (default 0)
