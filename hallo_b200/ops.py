@@ -220,7 +220,7 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torc
     return out
 
 
-@_timed(lambda q, *a, **kw: f"temporal_attention C{q.shape[1]//3 if False else a[2].shape[1]} rows{q.shape[0]}")
+@_timed(lambda q, k, v, out, **kw: f"temporal_attention C{out.shape[1]} rows{q.shape[0]} fk{kw.get('fk')}")
 def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, batch: int, fq: int,
                        fk: int, tokens: int, heads: int) -> torch.Tensor:
     """q/out: [batch*fq*tokens, ld]; k/v: [batch*fk*tokens, ldkv]."""
