@@ -16,6 +16,12 @@ static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
     // v2 (two query tiles per CTA, P in TMEM) when a frame has at least one full pair of tiles; the
     // single-tile kernel otherwise (small L) and for head_dim 160 at small L.
     case 40:
+      if (p->L >= 256 && !v1 && option(OPT_ATTN_V3) != 0) {     // register-S kernel (attn3_tc.cu), opt-in
+        if (poly == 4) return launch_attn3<T, 4>(p, s);
+        if (poly == 3) return launch_attn3<T, 3>(p, s);
+        if (poly == 2) return launch_attn3<T, 2>(p, s);
+        return launch_attn3<T, 0>(p, s);
+      }
       if (p->L >= 256 && !v1 && chunk_opt == 2) {
         if (poly == 4) return launch_attn2<T, 40, 128, 4, 32, true>(p, s);
         if (poly == 3) return launch_attn2<T, 40, 128, 3, 32, true>(p, s);

@@ -10,7 +10,7 @@ namespace hb {
 char g_last_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
 
-static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused"};
+static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "attn_v3"};
 static std::atomic<int> g_options[OPT_COUNT];
 static std::atomic<bool> g_options_init{false};
 

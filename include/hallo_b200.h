@@ -58,7 +58,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "xattn_tc"    1: tcgen05 cross-attention instead of the CUDA-core kernel                       (default 0)
  *   "tattn_mma"   1: temporal attention on warp-level tensor-core MMAs instead of CUDA cores      (default 0)
  *   "gemm_fill"   1: narrower GEMM N tiles (128 / 64) when the widest tile would leave SMs idle    (default 0)
- *   "gn_fused"    1: one-launch GroupNorm when a (frame, group) slab fits shared memory            (default 0) */
+ *   "gn_fused"    1: one-launch GroupNorm when a (frame, group) slab fits shared memory            (default 0)
+ *   "attn_v3"     1: head_dim-40 attention with Q K^T on mma.sync (scores in registers), P V on tcgen05 (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 

@@ -38,7 +38,7 @@ def test_kernel_selection_options_roundtrip():
     import __graft_entry__ as g
     g.build()
     from hallo_b200 import lib
-    for name in ("gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused"):
+    for name in ("gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "attn_v3"):
         if os.environ.get("HALLO_B200_" + name.upper()) is None:
             assert lib.get_option(name) == 0, name
         old = lib.get_option(name)

@@ -12,6 +12,7 @@ run() {   # name, env assignment, test files...
 run gemm_tepi  HALLO_B200_GEMM_TEPI=1  tests/test_gemm_gpu.py tests/test_aux_gpu.py tests/test_unet_gpu.py
 run attn_chunk HALLO_B200_ATTN_CHUNK=1 tests/test_attention_gpu.py tests/test_unet_gpu.py
 run attn_chunk2 HALLO_B200_ATTN_CHUNK=2 tests/test_attention_gpu.py tests/test_unet_gpu.py
+run attn_v3    HALLO_B200_ATTN_V3=1    tests/test_attention_gpu.py tests/test_unet_gpu.py
 run xattn_tc   HALLO_B200_XATTN_TC=1   tests/test_aux_gpu.py tests/test_unet_gpu.py
 run gemm_fill  HALLO_B200_GEMM_FILL=1  tests/test_gemm_gpu.py tests/test_aux_gpu.py tests/test_unet_gpu.py
 run gn_fused   HALLO_B200_GN_FUSED=1   tests/test_aux_gpu.py tests/test_unet_gpu.py
@@ -22,6 +23,9 @@ HALLO_B200_GEMM_TEPI=1 timeout 600 python tools/kbench.py gemm conv > gpurun_out
 HALLO_B200_ATTN_CHUNK=1 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk.log 2>&1
 HALLO_B200_ATTN_CHUNK=1 HALLO_B200_ATTN_POLY=4 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk_poly4.log 2>&1
 HALLO_B200_ATTN_CHUNK=2 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk2.log 2>&1
+HALLO_B200_ATTN_V3=1 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_v3.log 2>&1
+HALLO_B200_ATTN_V3=1 HALLO_B200_ATTN_POLY=4 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_v3_poly4.log 2>&1
+HALLO_B200_ATTN_V3=1 HALLO_B200_ATTN_POLY=3 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_v3_poly3.log 2>&1
 HALLO_B200_ATTN_CHUNK=2 HALLO_B200_ATTN_POLY=4 timeout 600 python tools/kbench.py attn > gpurun_out/exp_kbench_attn_chunk2_poly4.log 2>&1
 tail -n 30 gpurun_out/exp_kbench_*.log >> gpurun_out/exp_summary.txt
 cat gpurun_out/exp_summary.txt
