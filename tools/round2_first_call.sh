@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round: (1) default-path parity, (2) every staged switch on its own (parity + speed),
 # (3) op breakdown of a full step and of one rank's shard of an 8-rank job.  Everything lands in gpurun_out/.
-#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/round2_first_call.sh'
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider > gpurun_out/r2_tests_default.log 2>&1
 echo "default tests exit $?" | tee gpurun_out/r2_first_call_summary.txt
