@@ -87,6 +87,9 @@ class PackedWeights:
         # stem / head
         w_in = sd["conv_in.weight"]                                  # [C0, Cl, 3, 3] -> [C0, 64], k = tap*Cl + c
         c0, cl = w_in.shape[0], w_in.shape[1]
+        if 9 * cl > 64:
+            raise NotImplementedError(f"conv_in with {cl} input channels (use_landmark=True variant) is not implemented: "
+                                      "the im2col stem packs 9*in_channels <= 64 columns (Hallo ships in_channels=4)")
         wi = torch.zeros(c0, 64, dtype=w_in.dtype, device=w_in.device)
         wi[:, :9 * cl] = w_in.permute(0, 2, 3, 1).reshape(c0, 9 * cl)
         put("conv_in.w", wi)
@@ -206,10 +209,14 @@ class DenoiseEngine:
         self.level_hw = [(h >> i, w >> i) for i in range(nblk)]
         # scheduler state on the device
         self.step_idx = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.t_table = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        self.coef = torch.zeros(1, 4, dtype=torch.float32, device=self.dev)
+        # fixed-capacity, fixed-address tables: a captured graph holds these pointers, so schedules are copied IN PLACE
+        self.MAX_STEPS = 1024
+        self.t_table = torch.zeros(self.MAX_STEPS, dtype=torch.float32, device=self.dev)
+        self.coef = torch.zeros(self.MAX_STEPS, 4, dtype=torch.float32, device=self.dev)
         self.n_steps = 1
         self.guidance = 1.0
+        self._captured_with = None                       # (n_steps, guidance) baked into the graph as kernel arguments
+        assert self.nm + n_frames <= self.cfg.pe_max_len, "temporal length exceeds the positional-encoding table"
         self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
         self.model_out: Optional[torch.Tensor] = None
         self.sample: Optional[torch.Tensor] = None      # per-half fp32 sample for the plain forward() API path
@@ -236,6 +243,13 @@ class DenoiseEngine:
         if isinstance(cur, torch.Tensor):
             self.graph = None            # shapes changed: any captured graph is stale
         return self.window[key]
+
+    def _gn_ws(self) -> torch.Tensor:
+        """GroupNorm statistics workspace: 2 floats per (frame row, group or channel) -- sized from this engine's row
+        count and the widest (concatenated) channel count, not a constant."""
+        rows = max(self.nb * (self.nm + self.fl), 2 * (1 + self.nm))
+        cmax = 2 * max(self.cfg.block_out_channels)
+        return self.buf("gn_ws", 1, 2 * rows * (self.cfg.norm_num_groups + cmax), torch.float32)
 
     def L(self, level: int) -> int:
         hh, ww = self.level_hw[level]
@@ -316,22 +330,33 @@ class DenoiseEngine:
                     tt = f"{l.motion}.temporal_transformer"
                     C = b.channels
                     gn18 = self.buf(f"{l.motion}.gn18", nb * (nm + fl) * L, C)
-                    ws = self.buf("gn_ws", 1, 2 * 64 * (64 + 2560), torch.float32)
+                    ws = self._gn_ws()
                     ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
                                   n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
                                   fpb_in=nm, fpb_out=nm + fl, frame_off=0)
         torch.cuda.current_stream().synchronize()
 
     def set_schedule(self, timesteps: Sequence[int], coef: torch.Tensor, guidance: float):
-        self.n_steps = len(timesteps)
-        self.t_table = torch.tensor([float(t) for t in timesteps], dtype=torch.float32, device=self.dev)
-        self.coef = coef.to(self.dev, torch.float32).contiguous()
+        """Per-window schedule.  The tables keep their device addresses (a captured graph reads them); the step count
+        and the guidance scale are kernel ARGUMENTS of the captured launches, so changing them drops the graph."""
+        n = len(timesteps)
+        if n > self.MAX_STEPS:
+            raise ValueError(f"{n} inference steps exceed the engine's schedule capacity ({self.MAX_STEPS})")
+        self.n_steps = n
+        self.t_table[:n].copy_(torch.tensor([float(t) for t in timesteps], dtype=torch.float32))
+        self.coef[:n].copy_(coef.to(torch.float32).reshape(n, 4))
         self.guidance = float(guidance)
+        if self.graph is not None and self._captured_with != (self.n_steps, self.guidance):
+            self.graph = None
         self.step_idx.zero_()
+
+    def set_timestep(self, t: float):
+        """Single-forward API path (UNet3DConditionModel.forward): slot 0 of the table, in place."""
+        self.t_table[:1].fill_(float(t))
 
     # ------------------------------------------------------------------ modules
     def _gn(self, x1, name, out, n_frames, hw, eps, silu, x2=None, **kw):
-        ws = self.buf("gn_ws", 1, 2 * 64 * (64 + 2560), torch.float32)
+        ws = self._gn_ws()
         return ops.groupnorm(x1, self.W[f"{name}.w"], self.W[f"{name}.b"], out, ws, n_frames=n_frames, hw=hw,
                              groups=self.cfg.norm_num_groups, eps=eps, silu=silu, x2=x2, **kw)
 
@@ -706,6 +731,7 @@ class DenoiseEngine:
             self._forward()
             self._step_tail()
         self.graph = g
+        self._captured_with = (self.n_steps, self.guidance)
         self.latents.copy_(lat0)
         self.step_idx.copy_(st0)
 

@@ -84,5 +84,19 @@ class ReferenceAttentionControl:
         if self.mode == "read":
             self.unet.set_banks({})
         else:
+            # the pipeline builds a new writer per window (face_animate.py:300-313): drop this writer's pre-hooks with
+            # its banks, or every window would leave 16 more hooks (and norm1 + clone calls) on the ReferenceNet
             for m in self._writer_blocks:
                 m.bank.clear()
+            self.remove_hooks()
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    def __del__(self):
+        try:
+            self.remove_hooks()
+        except Exception:
+            pass

@@ -221,9 +221,14 @@ class UNet3DConditionModel(nn.Module):
             sample = 2 * sample - 1.0
         eng = self.engine(h, w, f)
         ms = None if motion_scale is None else tuple(float(x) for x in motion_scale)
-        wkey = tuple((id(t), t._version) for t in [encoder_hidden_states, audio_embedding, mask_cond_fea]
-                     + list(full_mask) + list(face_mask) + list(lip_mask)) + (ms, id(self._banks))
-        if wkey != self._window_key:
+        # window constants are re-hoisted unless every input is the SAME live object at the same version: the key holds
+        # strong references (an id() alone can be recycled by a new tensor after the old one is collected)
+        wins = [encoder_hidden_states, audio_embedding, mask_cond_fea] + list(full_mask) + list(face_mask) + list(lip_mask)
+        wkey = (wins, [None if t is None else t._version for t in wins], ms, self._banks)
+        old = self._window_key
+        same = old is not None and len(old[0]) == len(wins) and all(a is b for a, b in zip(old[0], wins)) \
+            and old[1] == wkey[1] and old[2] == ms and old[3] is self._banks
+        if not same:
             if mask_cond_fea is None:
                 mask_cond_fea = torch.zeros(b, self.arch.block_out_channels[0], f, h, w, device=sample.device,
                                             dtype=sample.dtype)
@@ -232,7 +237,7 @@ class UNet3DConditionModel(nn.Module):
                              motion_scale=ms, banks=self._banks)
             self._window_key = wkey
         t = float(timestep) if not torch.is_tensor(timestep) else float(timestep.reshape(-1)[0])
-        eng.t_table = torch.tensor([t], dtype=torch.float32, device=self.device)
+        eng.set_timestep(t)
         out = eng.forward_only(sample.float(), step=0).to(sample.dtype)
         if not return_dict:
             return (out,)

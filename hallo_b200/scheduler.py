@@ -14,6 +14,12 @@ import numpy as np
 import torch
 
 
+class DDIMSchedulerOutput:
+    def __init__(self, prev_sample, pred_original_sample=None):
+        self.prev_sample = prev_sample
+        self.pred_original_sample = pred_original_sample
+
+
 class DDIMScheduler:
     order = 1
     init_noise_sigma = 1.0
@@ -58,6 +64,28 @@ class DDIMScheduler:
 
     def scale_model_input(self, sample, timestep=None):
         return sample
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise=None, return_dict: bool = True):
+        """diffusers DDIMScheduler.step as the reference calls it (face_animate.py:420: v-prediction, eta 0):
+        x0 = sqrt(a_t) x - sqrt(1-a_t) v;  eps = sqrt(a_t) v + sqrt(1-a_t) x;  prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.
+        Host/PyTorch form of what `hallo_b200_cfg_ddim_step` does on the device -- kept so the scheduler object is a
+        complete stand-in at the call site (callbacks, custom loops); the engine's loop does not call it."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0 (stochastic DDIM) is not part of the reference configuration")
+        t = int(timestep)
+        prev = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t].to(torch.float64)
+        a_p = (self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod).to(torch.float64)
+        sa, sb = float(a_t.sqrt()), float((1 - a_t).sqrt())
+        x0 = sa * sample - sb * model_output
+        eps = sa * model_output + sb * sample
+        prev_sample = float(a_p.sqrt()) * x0 + float((1 - a_p).sqrt()) * eps
+        if not return_dict:
+            return (prev_sample,)
+        return DDIMSchedulerOutput(prev_sample=prev_sample, pred_original_sample=x0)
 
     def coef_table(self) -> torch.Tensor:
         """[n_steps, 4] = sqrt(a_t), sqrt(1 - a_t), sqrt(a_prev), sqrt(1 - a_prev) per inference step."""

@@ -26,7 +26,12 @@ from oracle import ref_host  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = [dict(h=8, f=2, seed=42, t=999, ms=(1.0, 0.9, 1.1)),
          dict(h=16, f=3, seed=43, t=499, ms=(1.0, 1.0, 1.0)),
-         dict(h=16, f=16, seed=44, t=24, ms=(1.2, 0.8, 1.0))]
+         dict(h=16, f=16, seed=44, t=24, ms=(1.2, 0.8, 1.0)),
+         # round 2: the shapes the bench actually times (L0 = 4096 with the 8192-key reference concat) and config-4's
+         # level sizes (L = 9216, 2304, 576, 144); run with `--only h64_f2 h64_f16 h96_f2` (f=16 takes ~3 min on 8 cores)
+         dict(h=64, f=2, seed=45, t=777, ms=(1.0, 0.7, 1.3)),
+         dict(h=64, f=16, seed=46, t=499, ms=(1.1, 0.9, 1.0)),
+         dict(h=96, f=2, seed=47, t=261, ms=(0.9, 1.1, 1.0))]
 
 
 def checksum(t: torch.Tensor) -> float:
@@ -34,6 +39,7 @@ def checksum(t: torch.Tensor) -> float:
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1:] if "--only" in sys.argv else None
     torch.set_num_threads(host_threads())
     os.makedirs(GOLD, exist_ok=True)
     cfg = UNetConfig()
@@ -46,6 +52,8 @@ def main():
     wsum = {k: checksum(sd[k]) for k in ("conv_in.weight", "mid_block.attentions.0.transformer_blocks.0.attn1.to_q.weight",
                                           "up_blocks.3.motion_modules.2.temporal_transformer.proj_out.weight")}
     for c in CASES:
+        if only is not None and f"h{c['h']}_f{c['f']}" not in only:
+            continue
         inp = synth_inputs(cfg, c["h"], c["h"], c["f"], seed=c["seed"], timestep=c["t"], motion_scale=c["ms"])
         ref_host.attach_reader(unet, inp["banks"])
         taps = {}
@@ -63,7 +71,8 @@ def main():
         out = ref_host.run_reference_unet(unet, inp)
         for hk in hooks:
             hk.remove()
-        fx = dict(case=c, out=out.clone(), taps=taps, weight_checksums=wsum,
+        # full-size outputs are stored in fp16 (rounding 5e-4 relative, far below the 1e-2 tolerance) to keep fixtures small
+        fx = dict(case=c, out=(out.clone() if out.numel() < (1 << 18) else out.half()), taps=taps, weight_checksums=wsum,
                   input_checksums=dict(sample=checksum(inp["sample"]), audio=checksum(inp["audio_embedding"]),
                                        bank0=checksum(inp["banks"]["mid_block.attentions.0"].float())),
                   torch_version=torch.__version__)

@@ -47,7 +47,10 @@ def _run(m, inp, dev):
     return out
 
 
-@pytest.mark.parametrize("name", ["unet_fwd_h8_f2.pt", "unet_fwd_h16_f3.pt", "unet_fwd_h16_f16.pt"])
+@pytest.mark.parametrize("name", ["unet_fwd_h8_f2.pt", "unet_fwd_h16_f3.pt", "unet_fwd_h16_f16.pt",
+                                  # round 2: the shapes bench.py times -- 64x64 latent: L0 = 4096 queries x 8192 keys with
+                                  # the reference concat, full 16-frame window (temporal length 18); 96x96 = config-4
+                                  "unet_fwd_h64_f2.pt", "unet_fwd_h64_f16.pt", "unet_fwd_h96_f2.pt"])
 def test_unet_forward_matches_reference_golden(model, name):
     from hallo_b200.spec import UNetConfig
     from hallo_b200.synth import synth_inputs
@@ -86,15 +89,16 @@ def test_strict_state_dict_and_api_surface(model):
     assert not m2_missing.missing_keys and not m2_missing.unexpected_keys
 
 
-@pytest.mark.xfail(reason="bf16 end-to-end path written after the round-1 GPU budget was spent; kernels are bf16-tested per op", strict=False)
-def test_unet_forward_bf16(model):
-    """config-4 dtype: bf16 storage / tensor-core inputs.  The reference's own bf16-vs-fp32 distance is 9.6e-3
-    (SURVEY.md 8c), so the tolerance against the fp32 golden is 3e-2."""
+@pytest.mark.parametrize("name", ["unet_fwd_h16_f3.pt", "unet_fwd_h96_f2.pt"])
+def test_unet_forward_bf16(model, name):
+    """config-4 dtype: bf16 storage / tensor-core inputs (banks arrive fp16-rounded per Q4, then bf16).  The reference's
+    own bf16-vs-fp32 distance is 9.6e-3 per forward, so the tolerance against the fp32 golden of the
+    unmodified reference is 2e-2 (SURVEY.md 8c "state the bf16 tolerance separately")."""
     from hallo_b200.spec import UNetConfig
     from hallo_b200.synth import synth_inputs
     m, sd = model
     dev = _dev()
-    fx = torch.load(os.path.join(GOLD, "unet_fwd_h16_f3.pt"), weights_only=False)
+    fx = torch.load(os.path.join(GOLD, name), weights_only=False)
     c = fx["case"]
     inp = synth_inputs(UNetConfig(), c["h"], c["h"], c["f"], seed=c["seed"], timestep=c["t"], motion_scale=c["ms"])
     try:
@@ -108,15 +112,13 @@ def test_unet_forward_bf16(model):
                 lip_mask=[t.to(dev, dt) for t in inp["lip_mask"]], motion_scale=inp["motion_scale"], return_dict=False)[0]
         torch.cuda.synchronize()
         err = rel_l2(out, fx["out"])
-        print(f"bf16: rel L2 vs reference fp32 = {err:.3e}")
-        assert err < 3e-2
+        print(f"bf16 {name}: rel L2 vs reference fp32 = {err:.3e}")
+        assert err < 2e-2
     finally:
         m.load_state_dict(sd, strict=True)          # restore exact fp16 weights for the other tests
         m.to(dtype=torch.float16)
 
 
-@pytest.mark.xfail(reason="added after the round-1 GPU budget was spent: ragged token counts (L = 2304, 576, 144, 36 -- the "
-                          "level sizes of the 768x768 config) have only been covered per kernel so far", strict=False)
 def test_unet_forward_matches_oracle_port_48x48_ragged(model):
     """Latent 48x48 / f=2: L is not a multiple of the 256-row attention tile pair (576 = 2.25 x 256, 144, 36), conv
     boxes overhang (24x24, 12x12, 6x6 images), temporal length 4."""

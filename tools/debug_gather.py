@@ -53,7 +53,7 @@ eng.begin_window(encoder_hidden_states=inp["encoder_hidden_states"].to(dev), aud
                  mask_cond_fea=inp["mask_cond_fea"].to(dev), full_mask=[m.to(dev) for m in inp["full_mask"]],
                  face_mask=[m.to(dev) for m in inp["face_mask"]], lip_mask=[m.to(dev) for m in inp["lip_mask"]],
                  motion_scale=inp["motion_scale"], banks={k: v.to(dev) for k, v in inp["banks"].items()})
-eng.t_table = torch.tensor([999.0], device=dev)
+eng.set_timestep(999.0)
 eng.latents.copy_(inp["sample"][:1, :, list(sh.frames)].to(dev))
 print(rank, "begin_window done", flush=True)
 for i in range(2):
@@ -67,7 +67,7 @@ eng1.begin_window(encoder_hidden_states=inp["encoder_hidden_states"].to(dev), au
                   mask_cond_fea=inp["mask_cond_fea"].to(dev), full_mask=[m.to(dev) for m in inp["full_mask"]],
                   face_mask=[m.to(dev) for m in inp["face_mask"]], lip_mask=[m.to(dev) for m in inp["lip_mask"]],
                   motion_scale=inp["motion_scale"], banks={k: v.to(dev) for k, v in inp["banks"].items()})
-eng1.t_table = torch.tensor([999.0], device=dev)
+eng1.set_timestep(999.0)
 eng1.latents.copy_(inp["sample"][:1].to(dev))
 eng1._forward()
 torch.cuda.synchronize()
