@@ -27,6 +27,9 @@
 namespace hb {
 
 constexpr int kAttn2Threads = 384;   // warpgroup 0: TMA / MMA / TMEM-alloc / idle; warpgroups 1, 2: softmax of tile A, B
+// MINB = 2 (two CTAs = four query tiles per SM, 64-key steps): no idle warps and no setmaxnreg -- ptxas allocates for
+// the launch bound (65536 / 2 / 320 -> 96 registers per thread), which the 64-column S row fits
+constexpr int kAttn2ThreadsOcc2 = 320;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 / 6-9 softmax of tile A / B
 
 template <int D, int BN>
 struct Attn2Cfg {
@@ -48,16 +51,8 @@ struct Attn2Cfg {
 };
 
 // POLY: every POLY-th exponential of a row goes to the FMA pipe (exp2_poly) instead of the SFU; 0 = all on the SFU
-// CHUNK: 0 = load the whole S row, then max, then exponentials (the hardware-tested schedule);
-//        32 = stream S through registers 32 columns at a time, the tcgen05.ld of chunk c+1 in flight while
-//             chunk c is exponentiated (online softmax per chunk, lazy rescale).  TMEM reads run at
-//             ~64 B/clk/SM, so the 64 KB S tile costs ~1000 clk -- as much as its 16 K exponentials on the
-//             SFU; serialised (CHUNK 0) the two add up, streamed they overlap.
-// ONES (head_dim 40 only, with CHUNK): the MMA warp writes 1.0 into column 40 of every V row (the columns 40..47 of
-//        the 48-wide PV tile are TMA zero fill), so O[:, 40] accumulates the softmax denominator on the tensor
-//        core -- with the same fp16-rounded P that builds O -- and the 128 FADD per row and step disappear.
-template <typename T, int D, int BN, int POLY, int CHUNK = 0, bool ONES = false>
-__global__ void __launch_bounds__(kAttn2Threads, 1)
+template <typename T, int D, int BN, int POLY, int MINB = 1>
+__global__ void __launch_bounds__(MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2, MINB)
 attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                 const __grid_constant__ CUtensorMap tmV1, const AttnDev p) {
@@ -106,14 +101,16 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<CF::kTmemCols>(tmem_slot);
+  constexpr int W0 = (MINB == 1) ? 4 : 2;          // first softmax warp
+  constexpr int kAllocWarp = (MINB == 1) ? 2 : 1;
+  if (warp == kAllocWarp) tmem_alloc<CF::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+  if (warp < W0) {
+    if (MINB == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
@@ -192,19 +189,6 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int t = 0; t < 2; ++t) {
         mbar_wait(&p_full[t], j & 1, 0x83);
         if (t == 0) mbar_wait(&v_full[vstage], vphase, 0x84);
-        if (ONES && t == 0) {
-          // column 40 = chunk 5 of the 128-byte row, 128B swizzle: chunk ^= row & 7
-          const uint16_t one = std::is_same<T, __half>::value ? (uint16_t)0x3C00 : (uint16_t)0x3F80;
-#pragma unroll
-          for (int i = 0; i < BN / 32; ++i) {
-            const uint32_t r = (uint32_t)lane + 32u * i;
-            asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(sV + vstage * CF::kKVBytes + r * 128u + ((5u ^ (r & 7u)) << 4)),
-                         "h"(one)
-                         : "memory");
-          }
-          fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's operand reads
-          __syncwarp();
-        }
         if (more && t == 0) mbar_wait(&k_full[kstage], kphase, 0x85);
         tc_fence_after();
         if (lane == 0) {
@@ -232,9 +216,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    if (MINB == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     // ============================ softmax warps ============================
-    const int t = (warp - 4) >> 2;                       // query tile of this warpgroup
+    const int t = (warp - W0) >> 2;                      // query tile of this group of four warps
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
@@ -243,7 +227,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_ref = -INFINITY;
     float l_sum = 0.f;
 
-    for (int j = 0; CHUNK == 0 && j < ntiles; ++j) {
+    for (int j = 0; j < ntiles; ++j) {
       const int kt = j % tiles_per_seg;
       const int key0 = kt * BN;
       mbar_wait(&s_full[t], j & 1, 0x91);
@@ -312,106 +296,10 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 
 
-    // ---- streamed variant: S row consumed in 32-column chunks, next chunk's TMEM load in flight ----
-    for (int j = 0; CHUNK != 0 && j < ntiles; ++j) {
-      constexpr int NCH = BN / 32;
-      const int kt = j % tiles_per_seg;
-      const int key0 = kt * BN;
-      const bool tail = (key0 + BN > p.L);
-      mbar_wait(&s_full[t], j & 1, 0x91);
-      tc_fence_after();
-      uint32_t buf[2][32];
-      uint32_t pk[BN / 2];                               // P, two keys per 32-bit TMEM column
-      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-      tmem_ld_x32(s_addr, buf[0]);
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        tmem_ld_wait();                                  // chunk c has landed in buf[c & 1]
-        if (c + 1 < NCH) tmem_ld_x32(s_addr + (c + 1) * 32, buf[(c + 1) & 1]);
-        const uint32_t(&sc)[32] = buf[c & 1];
-        float mx;
-        if (!tail) {
-          float m2[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m2[0] = max3(m2[0], __uint_as_float(sc[i]), __uint_as_float(sc[i + 1]));
-            m2[1] = max3(m2[1], __uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3]));
-          }
-          mx = fmaxf(m2[0], m2[1]);
-        } else {
-          mx = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + c * 32 + i < p.L) mx = fmaxf(mx, __uint_as_float(sc[i]));
-        }
-        mx *= p.scale_log2;
-        const bool need = (mx > m_ref + 8.0f);
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = fmaxf(m_ref, mx);
-          if (j > 0 || c > 0) {
-            // m_ref is finite here: key 0 of every K tile is in range, so chunk 0 of step 0 set it
-            const float f = fast_exp2(m_ref - m_new);
-            if (j > 0) {
-              // s_full(j) was committed after P_t V_{j-1}: O_t is quiescent (in-order tensor pipe)
-#pragma unroll
-              for (int cc = 0; cc < CF::kDv / 8; ++cc) {
-                uint32_t r[8];
-                tmem_ld_x8(o_addr + cc * 8, r);
-                tmem_ld_wait();                          // also retires the chunk load in flight
-#pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                tmem_st_x8(o_addr + cc * 8, r);
-              }
-            }
-            if (!ONES) {
-              l_sum *= f;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) ps4[q] *= f;
-            }
-#pragma unroll
-            for (int i = 0; i < c * 16; ++i) {           // P of the earlier chunks of this step
-              const float2 v = Cvt<T>::unpack2(pk[i]);
-              pk[i] = Cvt<T>::pack2(v.x * f, v.y * f);
-            }
-          }
-          m_ref = m_new;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float x0 = fmaf(__uint_as_float(sc[i]), p.scale_log2, -m_ref);
-          const float x1 = fmaf(__uint_as_float(sc[i + 1]), p.scale_log2, -m_ref);
-          constexpr int PM = POLY > 0 ? POLY : 1;
-          float e0 = (POLY > 0 && (i % PM) == PM - 1) ? exp2_poly(x0) : fast_exp2(x0);
-          float e1 = (POLY > 0 && ((i + 1) % PM) == PM - 1) ? exp2_poly(x1) : fast_exp2(x1);
-          if (tail) {
-            if (key0 + c * 32 + i >= p.L) e0 = 0.f;
-            if (key0 + c * 32 + i + 1 >= p.L) e1 = 0.f;
-          }
-          if (!ONES) ps4[(i >> 1) & 3] += e0 + e1;
-          pk[c * 16 + (i >> 1)] = Cvt<T>::pack2(e0, e1);
-        }
-      }
-      l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-#pragma unroll
-      for (int c = 0; c < BN / 64; ++c) tmem_st_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[c * 32]));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-
     // ---- epilogue: O / l -> global ----
     mbar_wait(&o_done[t], 0, 0x92);
     tc_fence_after();
-    float inv;
-    if (ONES) {
-      uint32_t r[8];
-      tmem_ld_x8(o_addr + 40, r);                      // O[:, 40] = sum of the (rounded) probabilities
-      tmem_ld_wait();
-      inv = 1.0f / __uint_as_float(r[0]);
-    } else {
-      inv = 1.0f / l_sum;
-    }
+    const float inv = 1.0f / l_sum;
     const int qrow = qt * 256 + t * 128 + row;
     T* out = reinterpret_cast<T*>(p.O) + ((long long)frame * p.L + qrow) * p.ldo + head * D;
 #pragma unroll
@@ -432,13 +320,13 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<CF::kTmemCols>(tmem_base);
   }
 }
 
-template <typename T, int D, int BN, int POLY, int CHUNK = 0, bool ONES = false>
+template <typename T, int D, int BN, int POLY, int MINB = 1>
 static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   using CF = Attn2Cfg<D, BN>;
   static_assert(CF::kTotal <= 232448, "attention v2 smem budget");
@@ -464,15 +352,14 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   d.O = q->O;
   d.ldo = q->ldo;
   d.scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  static_assert(!ONES || (D == 40 && CHUNK != 0), "ones column: head_dim 40, streamed softmax");
-  auto kern = attn2_tc_kernel<T, D, BN, POLY, CHUNK, ONES>;
+  auto kern = attn2_tc_kernel<T, D, BN, POLY, MINB>;
   static bool attr_set = false;
   if (!attr_set) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kTotal));
     attr_set = true;
   }
   dim3 grid((q->L + 255) / 256, q->heads, q->frames);
-  kern<<<grid, kAttn2Threads, CF::kTotal, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, d);
+  kern<<<grid, MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2, CF::kTotal, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, d);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

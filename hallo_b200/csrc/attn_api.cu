@@ -8,29 +8,16 @@ template <typename T>
 static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
   const bool v1 = option(OPT_ATTN_V1) != 0;     // A/B switches (hallo_b200_set_option / HALLO_B200_ATTN_*)
   const int poly = option(OPT_ATTN_POLY);
-  // streamed softmax (attn2_tc.cu, CHUNK = 32): written after the last GPU session of round 1, so it stays
-  // opt-in until tests/test_attention_gpu.py has passed with attn_chunk = 1 on hardware
-  const int chunk_opt = option(OPT_ATTN_CHUNK);   // 1: streamed softmax, 2: + row sums on the tensor core (d = 40)
-  const bool chunk = chunk_opt != 0;
+  const int occ2 = option(OPT_ATTN_OCC2);        // head_dim 40: 64-key steps, two CTAs (four query tiles) per SM
   switch (p->head_dim) {
     // v2 (two query tiles per CTA, P in TMEM) when a frame has at least one full pair of tiles; the
     // single-tile kernel otherwise (small L) and for head_dim 160 at small L.
     case 40:
-      if (p->L >= 256 && !v1 && option(OPT_ATTN_V3) != 0) {     // register-S kernel (attn3_tc.cu), opt-in
-        if (poly == 4) return launch_attn3<T, 4>(p, s);
-        if (poly == 3) return launch_attn3<T, 3>(p, s);
-        if (poly == 2) return launch_attn3<T, 2>(p, s);
-        return launch_attn3<T, 0>(p, s);
-      }
-      if (p->L >= 256 && !v1 && chunk_opt == 2) {
-        if (poly == 4) return launch_attn2<T, 40, 128, 4, 32, true>(p, s);
-        if (poly == 3) return launch_attn2<T, 40, 128, 3, 32, true>(p, s);
-        return launch_attn2<T, 40, 128, 0, 32, true>(p, s);
-      }
-      if (p->L >= 256 && !v1 && chunk) {
-        if (poly == 4) return launch_attn2<T, 40, 128, 4, 32>(p, s);
-        if (poly == 3) return launch_attn2<T, 40, 128, 3, 32>(p, s);
-        return launch_attn2<T, 40, 128, 0, 32>(p, s);
+      if (p->L >= 256 && !v1 && occ2 != 0) {
+        if (poly == 4) return launch_attn2<T, 40, 64, 4, 2>(p, s);
+        if (poly == 3) return launch_attn2<T, 40, 64, 3, 2>(p, s);
+        if (poly == 2) return launch_attn2<T, 40, 64, 2, 2>(p, s);
+        return launch_attn2<T, 40, 64, 0, 2>(p, s);
       }
       if (p->L >= 256 && !v1) {
         if (poly == 4) return launch_attn2<T, 40, 128, 4>(p, s);
@@ -40,7 +27,6 @@ static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
       }
       return launch_attn<T, 40, 128, 2>(p, s);
     case 80:
-      if (p->L >= 256 && !v1 && chunk) return launch_attn2<T, 80, 128, 0, 32>(p, s);
       if (p->L >= 256 && !v1) return launch_attn2<T, 80, 128, 0>(p, s);
       return launch_attn<T, 80, 64, 2>(p, s);
     case 160: return launch_attn<T, 160, 64, 2>(p, s);   // 2 x (2 S buffers + O) does not fit TMEM at d = 160

@@ -297,12 +297,19 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const T* __restrict__ x1,
   }
 }
 
+// seg > 0: rows are scattered by pixel slice -- pixel p of output frame n_out goes to base[p / seg] at row
+// n_out * seg + p % seg (the frame -> pixel ownership swap in front of a motion module; base[] are peer-mapped buffers)
+struct GnScatter {
+  void* base[HB_MAX_PEERS];
+  int seg;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1, int C1,
                                                        const T* __restrict__ x2, int C2, int HW,
                                                        int pix_per_cta, const float* __restrict__ scsh,
                                                        int silu, T* __restrict__ out, int fpb_in,
-                                                       int fpb_out, int frame_off) {
+                                                       int fpb_out, int frame_off, const GnScatter scat) {
   // thread (cv, py): fixed 8 channels, strided pixels -> per-channel scale/shift live in registers
   const int C = C1 + C2;
   const int nvec = C >> 3;
@@ -339,7 +346,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1,
       }
       o[j] = y;
     }
-    store8(dst + (long long)p * C, o);
+    if (scat.seg > 0) {
+      const int d = p / scat.seg;
+      store8(reinterpret_cast<T*>(scat.base[d]) + ((long long)n_out * scat.seg + (p - d * scat.seg)) * C + c0, o);
+    } else {
+      store8(dst + (long long)p * C, o);
+    }
   }
 }
 
@@ -780,10 +792,38 @@ extern "C" int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void*
   return HB_OK;
 }
 
+static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int C2, int N, int HW, int G,
+                          const void* gamma, const void* beta, float eps, int silu, void* out, float* stats_ws,
+                          int fpb_in, int fpb_out, int frame_off, const GnScatter& sc, hb_stream_t stream);
+
 extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, int N,
                                     int HW, int G, const void* gamma, const void* beta, float eps,
                                     int silu, void* out, float* stats_ws, int fpb_in, int fpb_out,
                                     int frame_off, hb_stream_t stream) {
+  GnScatter none{};
+  return groupnorm_impl(dtype, x1, C1, x2, C2, N, HW, G, gamma, beta, eps, silu, out, stats_ws, fpb_in, fpb_out,
+                        frame_off, none, stream);
+}
+
+extern "C" int hallo_b200_groupnorm_scatter(int dtype, const void* x1, int C1, int N, int HW, int G,
+                                            const void* gamma, const void* beta, float eps,
+                                            void* const* out_peers, int n_dest, float* stats_ws, int fpb_in,
+                                            int fpb_out, int frame_off, hb_stream_t stream) {
+  if (!out_peers || n_dest < 1 || n_dest > HB_MAX_PEERS || HW % n_dest != 0)
+    return fail(HB_ERR_BAD_SHAPE, "groupnorm_scatter: %d destinations for %d pixels", n_dest, HW);
+  GnScatter sc{};
+  for (int i = 0; i < n_dest; ++i) {
+    if (!out_peers[i]) return fail(HB_ERR_NULL, "groupnorm_scatter: null destination %d", i);
+    sc.base[i] = out_peers[i];
+  }
+  sc.seg = HW / n_dest;
+  return groupnorm_impl(dtype, x1, C1, nullptr, 0, N, HW, G, gamma, beta, eps, 0, out_peers[0], stats_ws, fpb_in,
+                        fpb_out, frame_off, sc, stream);
+}
+
+static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int C2, int N, int HW, int G,
+                          const void* gamma, const void* beta, float eps, int silu, void* out, float* stats_ws,
+                          int fpb_in, int fpb_out, int frame_off, const GnScatter& sc, hb_stream_t stream) {
   if (!x1 || !out || !gamma || !beta || !stats_ws) return fail(HB_ERR_NULL, "groupnorm: null pointer");
   const int C = C1 + C2;
   if (C1 % 8 || C2 % 8 || C % G || G > 64 || (C2 > 0 && !x2))
@@ -793,7 +833,7 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
     // one-launch path for slabs (HW x C/G halfs) that fit shared memory -- opt-in, see gn_fused_kernel
     const int cpg = C / G;
     const size_t slab = (size_t)HW * cpg * 2;
-    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024) {
+    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024 && sc.seg == 0) {
       if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
       const int vw = (cpg % 8 == 0) ? 4 : ((cpg % 4 == 0) ? 2 : 1);     // channel pairs per access (16 / 8 / 4 bytes)
       HB_DISPATCH_T(dtype, {
@@ -828,7 +868,7 @@ extern "C" int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const voi
     if (HW < ppc) ppc = HW;
     dim3 g2((HW + ppc - 1) / ppc, N);
     gn_apply_kernel<T><<<g2, threads, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, ppc, scsh, silu, (T*)out,
-                                              fpb_in, fpb_out, frame_off);
+                                              fpb_in, fpb_out, frame_off, sc);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;

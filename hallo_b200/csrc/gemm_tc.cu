@@ -54,6 +54,7 @@ struct GemmDev {
   const float* ln_colsum;
   float ln_eps;
   float* stats_out;
+  hb_row_scatter sc;   // sc.seg > 0: output rows go to peer buffers (direct epilogue only)
   // conv geometry
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
@@ -534,6 +535,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
       float osum = 0.f, osq = 0.f;
+      // destination of this lane's output row: local C, or (frame-sharded motion module) the owner rank's buffer
+      T* crow = C + row * p.ldc;
+      if (p.sc.seg > 0 && row_ok) {
+        const long long sg = row / p.sc.seg;
+        const long long qq = row - sg * p.sc.seg;
+        const long long dd = sg / p.sc.segs_per_dest;
+        const long long ii = sg - dd * p.sc.segs_per_dest;
+        crow = reinterpret_cast<T*>(p.sc.base[dd]) + (ii * p.sc.seg_stride + p.sc.row0 + qq) * p.ldc;
+      }
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
@@ -611,7 +621,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o4.y = Cvt<T>::pack2(o[j + 2], o[j + 3]);
               o4.z = Cvt<T>::pack2(o[j + 4], o[j + 5]);
               o4.w = Cvt<T>::pack2(o[j + 6], o[j + 7]);
-              *reinterpret_cast<uint4*>(C + row * p.ldc + ocol0 + j) = o4;
+              *reinterpret_cast<uint4*>(crow + ocol0 + j) = o4;
             }
           } else {
 #pragma unroll
@@ -631,7 +641,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 o4.y = Cvt<T>::pack2(w[2], w[3]);
                 o4.z = Cvt<T>::pack2(w[4], w[5]);
                 o4.w = Cvt<T>::pack2(w[6], w[7]);
-                *reinterpret_cast<uint4*>(C + row * p.ldc + col0 + j) = o4;
+                *reinterpret_cast<uint4*>(crow + col0 + j) = o4;
                 if (p.stats_out != nullptr) {
                   // statistics of the values as the next LayerNorm will read them (rounded to the storage type)
                   const float2 q0 = Cvt<T>::unpack2(o4.x), q1 = Cvt<T>::unpack2(o4.y), q2 = Cvt<T>::unpack2(o4.z),
@@ -711,6 +721,7 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   d.ln_colsum = q->ln_colsum;
   d.ln_eps = q->ln_eps;
   d.stats_out = q->stats_out;
+  if (q->scatter != nullptr) d.sc = *q->scatter;
   d.tiles_n = (q->N + BN - 1) / BN;
 
   CUtensorMap tmA, tmA2, tmB;
@@ -822,7 +833,7 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
   // has passed with gemm_tepi = 1 on hardware.  Needs whole N tiles and 16-byte aligned C / residual.
   const bool tepi_env = option(OPT_GEMM_TEPI) != 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p->C) | reinterpret_cast<uintptr_t>(p->residual)) & 15) == 0;
-  if (tepi_env && aligned) {
+  if (tepi_env && aligned && p->scatter == nullptr) {
     const bool geglu = (p->flags & HB_EPI_GEGLU) != 0;
     if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
     if (p->N % 192 == 0) return launch_gemm<T, 192, 6, 2, true>(p, s);
@@ -862,6 +873,11 @@ extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: ln_stats and ln_colsum go together (plain GEMM only)");
   if (p->stats_out != nullptr && (p->flags & HB_EPI_GEGLU))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: stats_out is not defined for the GEGLU epilogue");
+  if (p->scatter != nullptr && (p->residual != nullptr || p->conv3x3 || p->scatter->seg <= 0 ||
+                               p->scatter->segs_per_dest <= 0 ||
+                               (p->M + p->scatter->seg - 1) / p->scatter->seg > (long long)HB_MAX_PEERS * p->scatter->segs_per_dest))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: row scatter needs a plain GEMM without residual and <= %d destinations",
+                HB_MAX_PEERS);
   if (p->A2 != nullptr && (p->K1 % kBK != 0 || p->K1 <= 0 || p->K1 >= p->K || p->conv3x3))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: bad K split %d of %d", p->K1, p->K);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -10,7 +10,10 @@ namespace hb {
 char g_last_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
 
-static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "attn_v3"};
+static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_occ2", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused"};
+// defaults: the kernels promoted after their round-2 hardware runs (profiles/r2_first_call_*) are ON; setting an
+// option to 0 selects the previous-generation kernel (A/B measurements, shapes the new kernel does not cover)
+static const int kOptionDefaults[OPT_COUNT] = {1, 0, 0, 0, 0, 1, 1, 1, 1};
 static std::atomic<int> g_options[OPT_COUNT];
 static std::atomic<bool> g_options_init{false};
 
@@ -26,7 +29,7 @@ static void init_options() {
     env[n] = 0;
     const char* v = getenv(env);
     // a variable that is set but empty or non-numeric counts as 1 (the historical "defined = on" switches)
-    int val = 0;
+    int val = kOptionDefaults[i];
     if (v != nullptr) val = (*v >= '0' && *v <= '9') ? atoi(v) : 1;
     g_options[i].store(val, std::memory_order_relaxed);
   }
@@ -100,7 +103,9 @@ int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const
 
 extern "C" {
 
-int hallo_b200_abi_version(void) { return 1; }
+int hallo_b200_abi_version(void) { return 2; }
+int hallo_b200_sizeof_gemm_params(void) { return (int)sizeof(hb_gemm_params); }
+int hallo_b200_sizeof_attention_params(void) { return (int)sizeof(hb_attention_params); }
 
 const char* hallo_b200_last_error(void) { return hb::g_last_error; }
 

@@ -4,12 +4,11 @@
 #include "gemm_tc.cu"
 #include "attn_tc.cu"
 #include "attn2_tc.cu"
-#include "attn3_tc.cu"
 #include "attn_api.cu"
 #include "xattn_tc.cu"
 #include "tattn_mma.cu"
 #include "aux.cu"
-#include "ubench.cu"
+#include "peer.cu"
 
 extern "C" int hallo_b200_device_error(unsigned int* code_out) {
   unsigned int v = 0;

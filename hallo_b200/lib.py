@@ -35,7 +35,14 @@ class GemmParams(C.Structure):
         ("img_n", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p),
+        ("scatter", C.c_void_p),
     ]
+
+
+class RowScatter(C.Structure):
+    """hb_row_scatter (include/hallo_b200.h): output rows of a GEMM stored into per-destination (peer-mapped) buffers."""
+    _fields_ = [("base", C.c_void_p * 16), ("seg", C.c_int32), ("segs_per_dest", C.c_int32),
+                ("seg_stride", C.c_int64), ("row0", C.c_int64)]
 
 
 class AttentionParams(C.Structure):

@@ -41,25 +41,27 @@ enum hb_dtype { HB_F16 = 0, HB_BF16 = 1 };
  * Library info
  * ---------------------------------------------------------------------------------------- */
 int hallo_b200_abi_version(void);
+/* sizeof(hb_gemm_params) / sizeof(hb_attention_params) as compiled into the library: a binding written in another
+ * language asserts its own struct size against these before the first call (a short struct would be read past). */
+int hallo_b200_sizeof_gemm_params(void);
+int hallo_b200_sizeof_attention_params(void);
 const char* hallo_b200_last_error(void);
 /* Reads and clears the device-side error word written by a kernel that timed out on a barrier. */
 int hallo_b200_device_error(unsigned int* code_out);
 /* Number of kernel launches issued by this library since the last reset (bench.py gpu_launches). */
 int64_t hallo_b200_launch_count(int reset);
-/* Kernel-selection switches (A/B benchmarking and staged roll-out of new kernels; results are identical up to
- * rounding whatever the setting).  Each option starts from the environment variable HALLO_B200_<NAME> (upper
- * case) and can be changed at run time; unknown names return HB_ERR_BAD_SHAPE / -1.
- *   "gemm_tepi"   1: GEMM / conv epilogue staged through shared memory and written by TMA stores  (default 0)
- *   "gemm_1cta"   1: force the single-CTA GEMM kernel                                              (default 0)
- *   "attn_chunk"  1: attention streams S through registers in 32-column chunks; 2: and (head_dim 40)
- *                    accumulates the softmax row sums on the tensor core via a ones column in V    (default 0)
- *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU            (default 0)
- *   "attn_v1"     1: force the first-generation attention kernel                                   (default 0)
- *   "xattn_tc"    1: tcgen05 cross-attention instead of the CUDA-core kernel                       (default 0)
- *   "tattn_mma"   1: temporal attention on warp-level tensor-core MMAs instead of CUDA cores      (default 0)
- *   "gemm_fill"   1: narrower GEMM N tiles (128 / 64) when the widest tile would leave SMs idle    (default 0)
- *   "gn_fused"    1: one-launch GroupNorm when a (frame, group) slab fits shared memory            (default 0)
- *   "attn_v3"     1: head_dim-40 attention with Q K^T on mma.sync (scores in registers), P V on tcgen05 (default 0) */
+/* Kernel-selection switches (A/B measurements; results are identical up to rounding whatever the setting).  Each
+ * option starts from the environment variable HALLO_B200_<NAME> (upper case) or its default and can be changed at run
+ * time; unknown names return HB_ERR_BAD_SHAPE / -1.  Defaults are the kernels that won their hardware A/B run.
+ *   "gemm_tepi"   GEMM / conv epilogue staged through shared memory and written by TMA stores        (default 1)
+ *   "gemm_1cta"   force the single-CTA GEMM kernel                                                    (default 0)
+ *   "gemm_fill"   narrower GEMM N tiles (128 / 64) when the widest tile would leave SMs idle          (default 1)
+ *   "attn_occ2"   head_dim 40: 64-key steps and two CTAs (four query tiles) per SM                    (default 0)
+ *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU               (default 0)
+ *   "attn_v1"     force the single-tile attention kernel                                              (default 0)
+ *   "xattn_tc"    tcgen05 cross-attention (0: CUDA-core kernel)                                       (default 1)
+ *   "tattn_mma"   temporal attention on warp-level tensor-core MMAs (0: CUDA cores)                   (default 1)
+ *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 
@@ -126,7 +128,23 @@ typedef struct {
   /* fp32 [M,2]: atomically accumulates (sum, sum of squares) of every output row over the stored columns (zeroed by
    * the caller) -- feeds the next folded LayerNorm.  NULL = off. */
   float* stats_out;
+  /* Output-row scatter (multi-GPU, see "Peer memory" below): NULL = rows go to C + row*ldc.  Direct-store epilogue
+   * only; residual must be NULL. */
+  const struct hb_row_scatter* scatter;
 } hb_gemm_params;
+
+/* Output row r of the GEMM is split as s = r / seg, q = r % seg, d = s / segs_per_dest, i = s % segs_per_dest and
+ * stored at  base[d] + ((i * seg_stride + row0 + q) * ldc + col) elements  -- base[d] is a buffer of destination rank
+ * d (peer-mapped with hallo_b200_peer_open, or local).  Used by the motion module's proj_out (motion_module.py:312)
+ * of a frame-sharded window: the GEMM runs on (all frames x this rank's pixel slice) and its epilogue writes every
+ * (frame, pixel) row straight into the frame owner's buffer over NVLink -- the transfer IS the epilogue's store. */
+typedef struct hb_row_scatter {
+  void* base[16];
+  int32_t seg;
+  int32_t segs_per_dest;
+  int64_t seg_stride;
+  int64_t row0;
+} hb_row_scatter;
 
 int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream);
 
@@ -225,9 +243,41 @@ int hallo_b200_advance_step(int32_t* step, int n_steps, hb_stream_t stream);
 /* channels-last [B*F*HW, ld] (first C columns) -> fp32 [B, C, F, HW] (the reference's output layout). */
 int hallo_b200_tokens_to_bcfhw(int dtype, const void* x, int64_t ld, float* out, int B, int C, int F, int HW,
                                hb_stream_t stream);
+/* out = a + b over n elements (n % 8 == 0, 16-byte aligned): the residual add that closes a frame-sharded motion
+ * module (motion_module.py:313-315) once the peers' proj_out rows have landed. */
+int hallo_b200_add(int dtype, const void* a, const void* b, void* out, int64_t n, hb_stream_t stream);
 
-/* Instruction-throughput micro-benchmark (design evidence only; tools/ubench.py). Returns the thread count. */
-int hallo_b200_ubench_exp(int mode, int iters, float* scratch, hb_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Peer memory (multi-GPU, one process per GPU): the temporal attention of the motion modules
+ * (hallo/models/motion_module.py:579-609) mixes all frames of a pixel, everything else on the path is
+ * per-frame.  A frame-sharded window therefore swaps frame <-> pixel ownership around each motion
+ * module; the swap is FUSED into the producing kernels: the GroupNorm-apply that feeds the module and
+ * the module's proj_out GEMM store their rows directly into the destination rank's buffer over
+ * NVLink (peer-mapped device memory), two flag barriers per module replace the collectives.
+ *
+ * The one exception to "the library never allocates": exchange buffers must be cudaMalloc'ed
+ * allocations of their own to be exportable through CUDA IPC, so the library owns them.
+ * ---------------------------------------------------------------------------------------- */
+#define HB_MAX_PEERS 16
+#define HB_IPC_HANDLE_BYTES 64
+int hallo_b200_peer_alloc(int64_t bytes, void** ptr_out);                 /* cudaMalloc + zero fill */
+int hallo_b200_peer_free(void* ptr);
+int hallo_b200_peer_export(void* ptr, void* handle_out /* HB_IPC_HANDLE_BYTES, host */);
+int hallo_b200_peer_open(const void* handle /* host */, void** ptr_out);  /* maps another process's allocation */
+int hallo_b200_peer_close(void* ptr);
+/* Barrier over n ranks through flag words in peer memory.  flags[r] points at rank r's flag array (>= n uint32,
+ * zero-initialised; flags[me] is local, the others peer-mapped).  epoch: local device counter (uint32, starts 0),
+ * incremented by every call -- kept on the device so that a captured CUDA graph replays correctly.  Everything the
+ * calling stream wrote to peer memory before the barrier is visible to the peers' kernels after it.  A rank that
+ * waits longer than ~2 s records HB_ERR_DEVICE_TRAP in the device error word instead of hanging the GPU. */
+int hallo_b200_peer_barrier(void* const* flags /* host array of n device pointers */, int n, int me,
+                            uint32_t* epoch, hb_stream_t stream);
+/* hallo_b200_groupnorm whose output rows are scattered by pixel: pixel p of (remapped) frame n_out goes to
+ * out_peers[p / seg] + ((n_out * seg + p % seg) * C) elements, seg = HW / n_dest -- the frame -> pixel swap in front of
+ * a motion module (motion_module.py:290-296), fused into the GroupNorm's store. */
+int hallo_b200_groupnorm_scatter(int dtype, const void* x1, int C1, int N, int HW, int G, const void* gamma,
+                                 const void* beta, float eps, void* const* out_peers /* host array */, int n_dest,
+                                 float* stats_ws, int fpb_in, int fpb_out, int frame_off, hb_stream_t stream);
 
 #ifdef __cplusplus
 }

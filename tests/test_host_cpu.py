@@ -23,7 +23,24 @@ def test_c_abi_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(cdll, n)]
     assert not missing, missing
     cdll.hallo_b200_abi_version.restype = ctypes.c_int
-    assert cdll.hallo_b200_abi_version() == 1
+    assert cdll.hallo_b200_abi_version() == 2
+    assert not any("ubench" in n for n in names), "micro-benchmarks are not part of the public ABI"
+
+
+def test_ctypes_structs_match_the_compiled_header():
+    """The ctypes mirrors in hallo_b200/lib.py (and the copy shown in INTEGRATION.md) must have exactly the size the
+    library was compiled with; a short struct would make the library read past the caller's memory."""
+    import __graft_entry__ as g
+    g.build()
+    from hallo_b200 import lib
+    h = lib.load()
+    assert ctypes.sizeof(lib.GemmParams) == h.hallo_b200_sizeof_gemm_params()
+    assert ctypes.sizeof(lib.AttentionParams) == h.hallo_b200_sizeof_attention_params()
+    # the struct printed in INTEGRATION.md: same field names, in the same order, as the binding the repo itself uses
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class GemmParams"):doc.index("def linear")]
+    doc_fields = re.findall(r'\("([A-Za-z0-9_]+)",\s*C\.c_', block)
+    assert doc_fields == [f[0] for f in lib.GemmParams._fields_], doc_fields
 
 
 def test_no_undefined_names_in_gpu_only_code():
@@ -34,21 +51,25 @@ def test_no_undefined_names_in_gpu_only_code():
 
 
 def test_kernel_selection_options_roundtrip():
-    """hallo_b200_set_option / get_option are host-only: defaults keep every hardware-untested kernel switched off."""
+    """hallo_b200_set_option / get_option are host-only; the defaults are the kernels promoted after their hardware
+    A/B runs (profiles/r2_first_call_summary.txt), everything still experimental stays off."""
     import __graft_entry__ as g
     g.build()
     from hallo_b200 import lib
-    for name in ("gemm_tepi", "gemm_1cta", "attn_chunk", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "attn_v3"):
+    defaults = {"gemm_tepi": 1, "gemm_1cta": 0, "gemm_fill": 1, "attn_occ2": 0, "attn_poly": 0, "attn_v1": 0,
+                "xattn_tc": 1, "tattn_mma": 1, "gn_fused": 1}
+    for name, dflt in defaults.items():
         if os.environ.get("HALLO_B200_" + name.upper()) is None:
-            assert lib.get_option(name) == 0, name
+            assert lib.get_option(name) == dflt, name
         old = lib.get_option(name)
         lib.set_option(name, 3)
         assert lib.get_option(name) == 3
         lib.set_option(name, old)
     with pytest.raises(RuntimeError):
         lib.set_option("no_such_option", 1)
-    with pytest.raises(KeyError):
-        lib.get_option("no_such_option")
+    for gone in ("no_such_option", "attn_chunk", "attn_v3"):          # losers of the A/B runs were deleted
+        with pytest.raises(KeyError):
+            lib.get_option(gone)
 
 
 def test_no_cpu_fallback_in_product_path():

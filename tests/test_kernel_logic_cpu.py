@@ -2,8 +2,7 @@
  * the lane-level fragment arithmetic of hallo_b200/csrc/tattn_mma.cu (ldmatrix / mma.sync m16n8k16 layouts per the
    PTX ISA) reproduces softmax(Q K^T / sqrt(d)) V for every (pixel, head) task, including ragged frame counts, the
    half-filled last k-step of head_dim 40 and the uninitialised row padding;
- * the streamed (32-column chunk) online softmax with lazy rescale of hallo_b200/csrc/attn2_tc.cu (CHUNK = 32) is
-   algebraically the plain softmax.
+ * the panel assignment and 64B-swizzle addressing of the GEMM's TMA-store epilogue (gemm_tc.cu, TEPI).
 These are restatements of the kernels' control flow in numpy, not the kernels themselves; the GPU parity tests
 remain the gate."""
 import numpy as np
@@ -149,65 +148,6 @@ def test_tattn_mma_fragment_logic(D, Fq, Fk, heads, pix):
 
 
 # ------------------------------------------------------------------------------------------------ streamed softmax
-def _streamed_attention_row(srows, v, scale_log2, L, BN=128, threshold=8.0):
-    """One query row of attn2_tc_kernel<CHUNK=32>: K tiles of BN keys, each consumed in 32-column chunks; running
-    reference max m_ref raised only when a chunk maximum exceeds it by > threshold (log2 units)."""
-    m_ref, l_sum = -np.inf, 0.0
-    o = np.zeros(v.shape[1])
-    ntiles = (L + BN - 1) // BN
-    for j in range(ntiles):
-        key0 = j * BN
-        s = np.full(BN, 1e30)                                   # out-of-range columns hold garbage
-        n_valid = min(BN, L - key0)
-        s[:n_valid] = srows[key0:key0 + n_valid]
-        tail = key0 + BN > L
-        pk = np.zeros(BN)
-        ps = 0.0
-        for c in range(BN // 32):
-            sc = s[c * 32:(c + 1) * 32]
-            if not tail:
-                mx = sc.max()
-            else:
-                valid = [sc[i] for i in range(32) if key0 + c * 32 + i < L]
-                mx = max(valid) if valid else -np.inf
-            mx *= scale_log2
-            if mx > m_ref + threshold:
-                m_new = max(m_ref, mx)
-                if j > 0 or c > 0:
-                    f = 2.0 ** (m_ref - m_new)
-                    if j > 0:
-                        o *= f
-                    l_sum *= f
-                    ps *= f
-                    pk[:c * 32] *= f
-                m_ref = m_new
-            e = 2.0 ** (sc * scale_log2 - m_ref)
-            if tail:
-                e = np.where(key0 + c * 32 + np.arange(32) >= L, 0.0, e)
-            ps += e.sum()
-            pk[c * 32:(c + 1) * 32] = e
-        l_sum += ps
-        vv = np.zeros((BN, v.shape[1]))
-        vv[:n_valid] = v[key0:key0 + n_valid]                    # TMA zero-fills rows past L
-        o += pk @ vv
-    return o / l_sum
-
-
-@pytest.mark.parametrize("L,spread", [(256, 1.0), (300, 30.0), (1000, 200.0), (128, 0.01)])
-def test_streamed_softmax_with_lazy_rescale_is_softmax(L, spread):
-    rng = np.random.default_rng(L)
-    d = 40
-    s = rng.standard_normal(L) * spread
-    s[rng.integers(0, L, 5)] += 3 * spread                       # late large scores force rescales mid-tile
-    v = rng.standard_normal((L, d))
-    scale_log2 = 1.4426950408889634 / np.sqrt(d)
-    got = _streamed_attention_row(s, v, scale_log2, L)
-    w = np.exp((s - s.max()) / np.sqrt(d))
-    ref = (w / w.sum()) @ v
-    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
-
-
-# ------------------------------------------------------------------------------------------------ TMA-store epilogue
 def _tepi_cover(BN, geglu):
     """Panel / unit assignment of gemm_tc_kernel<TEPI> (hallo_b200/csrc/gemm_tc.cu): returns, per output column of a
     tile, how many times it is written, and per accumulator column how many times it is read."""
@@ -259,87 +199,3 @@ def test_tepi_swizzle64_is_bank_conflict_free_and_bijective():
 
 
 # ------------------------------------------------------------------------------------------------ attn3 (register S)
-def _attn3_warp_step_model(wq, seed):
-    """One compute warp of attn3_tc_kernel for one 128-key step: Q / K fragments by ldmatrix from 128B-swizzled
-    [rows][64 halfs] tiles, S on mma.sync, P packed and written with tcgen05.st.16x128b.x8 (layout per the CuTe
-    SM100_TMEM_STORE_16dp128b8x traits: lane (g,t), regs 2i / 2i+1 -> lanes g / g+8, column 4i + t), consumed by a
-    TS-MMA that reads row r from TMEM lane r and key k from the 16-bit half (k & 1) of column k // 2."""
-    rng = np.random.default_rng(seed)
-    D, BN = 40, 128
-    Q = np.zeros((128, 64)); K = np.zeros((BN, 64))
-    Q[:, :D] = rng.standard_normal((128, D)); K[:, :D] = rng.standard_normal((BN, D))      # columns 40..63: TMA zero fill
-
-    def swz_tile(M):                                   # [rows][64] -> flat smem halves with the 128B swizzle
-        sm = np.full(M.shape[0] * 64, np.nan)
-        for r in range(M.shape[0]):
-            for c in range(8):
-                dst = r * 64 + ((c ^ (r & 7)) * 8)
-                sm[dst:dst + 8] = M[r, c * 8:c * 8 + 8]
-        return sm
-
-    sQ, sK = swz_tile(Q), swz_tile(K)
-    qa = [[None] * 3 for _ in range(2)]
-    for mt in range(2):
-        for ks in range(3):
-            addrs = []
-            for l in range(32):
-                row = wq * 32 + mt * 16 + (l & 7) + ((l >> 3) & 1) * 8
-                chunk = 2 * ks + (l >> 4)
-                addrs.append(row * 128 + ((chunk ^ (row & 7)) << 4))
-            qa[mt][ks] = _ldsm(sQ, addrs, 4)
-    s = [[[[0.0] * 4 for _ in range(32)] for _ in range(16)] for _ in range(2)]
-    for np_ in range(8):
-        for ks in range(3):
-            addrs = []
-            for l in range(32):
-                key = np_ * 16 + ((l >> 4) & 1) * 8 + (l & 7)
-                chunk = 2 * ks + ((l >> 3) & 1)
-                addrs.append(key * 128 + ((chunk ^ (key & 7)) << 4))
-            kb = _ldsm(sK, addrs, 4)
-            b0 = [[kb[l][0], kb[l][1]] for l in range(32)]
-            b1 = [[kb[l][2], kb[l][3]] for l in range(32)]
-            for mt in range(2):
-                _mma(s[mt][2 * np_], qa[mt][ks], b0)
-                _mma(s[mt][2 * np_ + 1], qa[mt][ks], b1)
-    Sref = Q @ K.T
-    for mt in range(2):
-        for nt in range(16):
-            for l in range(32):
-                g, t = l >> 2, l & 3
-                for hh in range(2):
-                    for e in range(2):
-                        assert abs(s[mt][nt][l][hh * 2 + e] - Sref[wq * 32 + mt * 16 + g + 8 * hh, nt * 8 + 2 * t + e]) < 1e-9
-    # P := S (any per-element function works for the layout check); pk[mt][nt*2+hh] = (cols 2t, 2t+1 of row g + 8hh)
-    tmem = {}
-    for mt in range(2):
-        for half in range(2):                          # two x8 stores: keys 0..63 / 64..127
-            base_lane, c0 = wq * 32 + mt * 16, 32 * half
-            for l in range(32):
-                g, t = l >> 2, l & 3
-                for i in range(8):                     # register pair i of this store = 8-key tile nt
-                    nt = half * 8 + i
-                    for hh in range(2):                # regs[2i + hh] = pk[mt][half*16 + 2i + hh] = pk[mt][nt*2 + hh]
-                        tmem[(base_lane + g + 8 * hh, c0 + 4 * i + t)] = (s[mt][nt][l][hh * 2], s[mt][nt][l][hh * 2 + 1])
-    for r in range(wq * 32, wq * 32 + 32):
-        for k in range(BN):
-            assert abs(tmem[(r, k // 2)][k & 1] - Sref[r, k]) < 1e-9, (r, k)
-    # rescale-factor routing: the factor of row 32 wq + L is held by quad (L & 7) in slot [L >> 4][(L >> 3) & 1]
-    f = [[[10 * mt + hh + 0.01 * (l >> 2) for hh in range(2)] for mt in range(2)] for l in range(32)]   # f[lane][mt][hh]
-    for L in range(32):
-        src = (L & 7) * 4
-        fr = f[src][1][1] if (L & 16 and L & 8) else f[src][1][0] if (L & 16) else f[src][0][1] if (L & 8) else f[src][0][0]
-        mt, hh, g = L >> 4, (L >> 3) & 1, L & 7
-        assert fr == 10 * mt + hh + 0.01 * g           # = factor of fragment row (mt, hh, g) = tile row 16 mt + 8 hh + g = L
-
-
-@pytest.mark.parametrize("wq", [0, 1, 2, 3])
-def test_attn3_fragment_and_tmem_store_layout(wq):
-    _attn3_warp_step_model(wq, seed=wq)
-
-
-def test_attn3_ones_column_address():
-    """V tile: [128 keys][64 halfs], 128B swizzle; element (key r, column 40) = chunk 5, first half of the chunk."""
-    for r in range(128):
-        byte = r * 128 + ((5 ^ (r & 7)) << 4)
-        logical = (r * 128 + 40 * 2)
-        assert byte == logical ^ (((logical >> 7) & 7) << 4)

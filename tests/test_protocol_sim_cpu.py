@@ -183,99 +183,3 @@ def test_gemm_tepi_epilogue_protocol(panels, has_res):
     for ntiles in (1, 2, 3, 5):
         for seed in range(25):
             _tepi_protocol(ntiles, panels, has_res, seed)
-
-
-def _attn3_protocol(ntiles, seed, rescale_prob=0.3):
-    """attn3_tc_kernel: TMA warp, tcgen05 issuer, 2 tiles x 4 compute warps; K/V rings of 2, P double-buffered per tile."""
-    import random
-    sim = Sim(seed)
-    rng = random.Random(seed * 7 + 1)
-    ST = 2
-    k_full = [Bar(1) for _ in range(ST)]; k_empty = [Bar(8) for _ in range(ST)]
-    v_full = [Bar(1) for _ in range(ST)]; v_empty = [Bar(1) for _ in range(ST)]
-    p_full = [Bar(4) for _ in range(4)]; p_free = [Bar(1) for _ in range(4)]; o_done = [Bar(1), Bar(1)]
-    Kst = [None] * ST; Vst = [None] * ST; k_reads = [0] * ST
-    P = [dict(step=None, writers=0, consumed=True) for _ in range(4)]
-    pv_done = [-1, -1]                     # last completed P V step per tile
-    pv_inflight = [False, False]
-
-    def tma():
-        stage, phase = 0, 0
-        for j in range(ntiles):
-            yield ('wait', k_empty[stage], phase ^ 1)
-            assert Kst[stage] is None or k_reads[stage] == 8, f"K stage {stage} overwritten with {k_reads[stage]} readers done"
-            k_full[stage].arrive(tx=1)
-            def kland(s=stage, j=j):
-                Kst[s] = j; k_reads[s] = 0; k_full[s].complete_tx(1)
-            sim.later(kland)
-            yield ('wait', v_empty[stage], phase ^ 1)
-            v_full[stage].arrive(tx=1)
-            def vland(s=stage, j=j):
-                Vst[s] = j; v_full[s].complete_tx(1)
-            sim.later(vland)
-            yield ('step',)
-            stage += 1
-            if stage == ST: stage, phase = 0, phase ^ 1
-
-    def umma():
-        vstage, vphase = 0, 0
-        for j in range(ntiles):
-            buf, bph = j & 1, (j >> 1) & 1
-            for t in range(2):
-                if t == 0:
-                    yield ('wait', v_full[vstage], vphase)
-                    assert Vst[vstage] == j
-                yield ('wait', p_full[t * 2 + buf], bph)
-                pb = P[t * 2 + buf]
-                assert pb['step'] == j and pb['writers'] == 4, f"PV({t},{j}) reads P buffer {pb}"
-                pv_inflight[t] = True
-                def done(t=t, j=j, pb=pb, vs=vstage):
-                    assert Vst[vs] == j, f"PV({t},{j}) read V stage holding {Vst[vs]}"
-                    pb['consumed'] = True; pv_done[t] = j; pv_inflight[t] = False
-                sim.later(done, 'tc')
-                sim.later(lambda b=p_free[t * 2 + buf]: b.arrive(), 'tc')
-                if j + 1 == ntiles:
-                    sim.later(lambda b=o_done[t]: b.arrive(), 'tc')
-                if t == 1:
-                    sim.later(lambda b=v_empty[vstage]: b.arrive(), 'tc')
-                yield ('step',)
-            vstage += 1
-            if vstage == ST: vstage, vphase = 0, vphase ^ 1
-
-    def compute(t, w):
-        kstage, kphase = 0, 0
-        for j in range(ntiles):
-            buf = j & 1
-            yield ('wait', k_full[kstage], kphase)
-            assert Kst[kstage] == j, f"tile {t} warp {w} step {j} read K stage holding {Kst[kstage]}"
-            k_reads[kstage] += 1
-            yield ('step',)
-            k_empty[kstage].arrive()
-            kstage += 1
-            if kstage == ST: kstage, kphase = 0, kphase ^ 1
-            if j > 0 and rng.random() < rescale_prob:
-                yield ('wait', p_free[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1)
-                assert pv_done[t] == j - 1 and not pv_inflight[t], f"rescale at step {j} with P V state {pv_done[t]}"
-                yield ('step',)
-            yield ('wait', p_free[t * 2 + buf], ((j >> 1) & 1) ^ 1)
-            pb = P[t * 2 + buf]
-            if pb['step'] != j:
-                assert pb['consumed'], f"tile {t} step {j} overwrites unconsumed P buffer {pb}"
-                pb.update(step=j, writers=0, consumed=False)
-            pb['writers'] += 1
-            yield ('step',)
-            p_full[t * 2 + buf].arrive()
-        yield ('wait', o_done[t], 0)
-        assert pv_done[t] == ntiles - 1
-
-    sim.add('tma', tma()); sim.add('umma', umma())
-    for t in range(2):
-        for w in range(4):
-            sim.add(f't{t}w{w}', compute(t, w))
-    sim.run()
-
-
-@pytest.mark.parametrize("ntiles", [1, 2, 3, 4, 7])
-def test_attn3_protocol(ntiles):
-    for seed in range(60):
-        _attn3_protocol(ntiles, seed)

@@ -1,6 +1,13 @@
 // Micro-benchmarks of instruction throughput that drive kernel design decisions (not on the product path).
-#include "host_common.cuh"
-#include "ptx.cuh"
+// Built by __graft_entry__.build() into tools/libhb_ubench.so -- a design-evidence tool, NOT part of libhallo_b200.so
+// nor of include/hallo_b200.h.
+#include "../hallo_b200/csrc/host_common.cuh"
+#include "../hallo_b200/csrc/ptx.cuh"
+
+namespace hb {   // this standalone library carries its own copies of the two host globals it touches
+char g_last_error[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+}
 
 namespace hb {
 
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(256) ubench_tmem_ld_kernel(float* out, int ite
 }  // namespace hb
 
 // returns ops (thread-level instructions) executed per launch; caller times it
-extern "C" int hallo_b200_ubench_exp(int mode, int iters, float* scratch, hb_stream_t stream) {
+extern "C" int hb_ubench_exp(int mode, int iters, float* scratch, hb_stream_t stream) {
   using namespace hb;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = num_sms() * 8;

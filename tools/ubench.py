@@ -11,18 +11,18 @@ from hallo_b200 import lib  # noqa: E402
 NAMES = {0: "ex2.approx.ftz.f32", 1: "ex2.approx.ftz.f16x2", 2: "ex2.approx.ftz.bf16x2", 3: "fma.rn.f32 (3-reg)",
          4: "max.f32", 5: "cvt.rn.f16x2.f32", 6: "add.f32", 7: "mma.sync.m16n8k16.f16 (per-thread count)",
          8: "tcgen05.ld.32x32b.x32 (per-thread count)"}
-h = lib.load()
+h = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhb_ubench.so"))
 scratch = torch.zeros(16, device="cuda")
 iters = 4096
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 clk = 1.965e9
 for mode, name in NAMES.items():
     for _ in range(2):
-        n = h.hallo_b200_ubench_exp(C.c_int(mode), C.c_int(iters), C.c_void_p(scratch.data_ptr()), lib.current_stream())
+        n = h.hb_ubench_exp(C.c_int(mode), C.c_int(iters), C.c_void_p(scratch.data_ptr()), lib.current_stream())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    n = h.hallo_b200_ubench_exp(C.c_int(mode), C.c_int(iters), C.c_void_p(scratch.data_ptr()), lib.current_stream())
+    n = h.hb_ubench_exp(C.c_int(mode), C.c_int(iters), C.c_void_p(scratch.data_ptr()), lib.current_stream())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
