@@ -79,14 +79,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _hard_exit():
-    """Multi-rank runs leave through os._exit: destroy_process_group() blocks for minutes when CUDA graphs that
-    captured NCCL collectives are still alive (measured: profiles/r1_debug_gather_2gpu.log)."""
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
-
-
 def plan_shard(rank: int, world: int, n_frames: int):
     from hallo_b200.dist import plan_shard as ps
     return ps(rank, world, n_frames)
@@ -178,7 +170,7 @@ def main():
     K, Wm = args.steps, max(args.warmup, 0)
     config = {"workload": f"{args.size * 8}x{args.size * 8}, {args.frames}-frame window, CFG batch 2, "
                           f"{N_DDIM}-step DDIM (configs[1])", "latent": [2, 4, args.frames, args.size, args.size],
-              "parallelism": f"cfg-half x frame-shard over {world} rank(s)",
+              "parallelism": f"frame-shard (both CFG halves per rank) over {world} rank(s)",
               "l2": "per-step working set >> 126 MB L2, no explicit flush"}
 
     if args.impl == "reference":
@@ -226,8 +218,8 @@ def main():
     if args.emulate_shard > 1 and world == 1:
         from hallo_b200.dist import shard_layout
         from hallo_b200.engine import Shard
-        halves, frames_ = shard_layout(args.emulate_shard, args.frames)[args.emulate_shard // 2]   # first cond-half rank
-        shard = Shard(halves=halves, frames=frames_, emulate_group=max(1, args.emulate_shard // 2))
+        halves, frames_ = shard_layout(args.emulate_shard, args.frames)[0]
+        shard = Shard(halves=halves, frames=frames_, emulate_group=args.emulate_shard)
         config["emulated_rank_of"] = args.emulate_shard
     eng = DenoiseEngine(W, args.size, args.size, args.frames, shard)
     # record the kernel-selection switches this line was measured with (defaults = the kernels that won their hardware A/B runs)
@@ -236,9 +228,10 @@ def main():
                                                               "attn_v1", "xattn_tc", "tattn_mma", "gn_fused")}
     except Exception:
         pass
-    if world > 2:
-        config["temporal_exchange"] = ("all-to-all frame<->pixel around each motion module" if eng.motion_a2a
-                                       else "NCCL all-gather of the temporal K/V")
+    if world > 1:
+        config["temporal_exchange"] = ("frame<->pixel swap around each motion module, fused into the producing kernels' "
+                                       "stores over peer memory + flag barriers" if shard.exchange == "peer"
+                                       else "frame<->pixel swap around each motion module, NCCL all_to_all_single")
     sch = DDIMScheduler()
     sch.set_timesteps(N_DDIM)
 
@@ -246,9 +239,12 @@ def main():
     def pin(t):
         return t.to(dt if t.is_floating_point() and t.dtype != torch.float16 else t.dtype).contiguous().pin_memory()
 
-    host = dict(encoder_hidden_states=pin(inp["encoder_hidden_states"]), audio_embedding=pin(inp["audio_embedding"]),
-                mask_cond_fea=pin(inp["mask_cond_fea"]), full_mask=[pin(m) for m in inp["full_mask"]],
-                face_mask=[pin(m) for m in inp["face_mask"]], lip_mask=[pin(m) for m in inp["lip_mask"]],
+    # a rank only needs its own frames of the per-frame tensors: slice on the host, so the e2e leg's H2D is the shard's
+    fr = list(shard.frames)
+    rows = [b * args.frames + g for b in (0, 1) for g in fr]
+    host = dict(encoder_hidden_states=pin(inp["encoder_hidden_states"]), audio_embedding=pin(inp["audio_embedding"][:, fr]),
+                mask_cond_fea=pin(inp["mask_cond_fea"][:, :, fr]), full_mask=[pin(m[rows]) for m in inp["full_mask"]],
+                face_mask=[pin(m[rows]) for m in inp["face_mask"]], lip_mask=[pin(m[rows]) for m in inp["lip_mask"]],
                 banks={k: v.contiguous().pin_memory() for k, v in inp["banks"].items()})
     lat_host = inp["sample"][:1, :, list(shard.frames)].float().contiguous().pin_memory()
     lat_back = torch.empty_like(lat_host).pin_memory()
@@ -263,7 +259,7 @@ def main():
         d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else
                  ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else
                   {kk: t.to(dev, non_blocking=True) for kk, t in v.items()})) for k, v in host.items()}
-        eng.begin_window(motion_scale=inp["motion_scale"], **d)
+        eng.begin_window(motion_scale=inp["motion_scale"], local_frames=True, **d)
 
     begin_window_from_host()
     eng.set_schedule(sch.timesteps.tolist(), sch.coef_table(), 3.5)
@@ -359,11 +355,26 @@ def main():
         eng.graph = eng.graph_saved
         barrier()
 
+    # ---------------- N > 1: the sharded run must reproduce the unsharded engine (collective; rank 0 holds the answer) ----
+    shard_err = None
+    if world > 1:
+        from hallo_b200.dist import sharded_vs_unsharded
+        shard_err = sharded_vs_unsharded(eng, inp, steps=2, use_graph=eng.graph is not None)
+
+    def orderly_exit():
+        """Graphs first (a live graph holding NCCL work is what hung destroy_process_group in round 1), then the peer
+        mappings, then the process group."""
+        import torch.distributed as dist
+        eng.graph = None
+        torch.cuda.synchronize()
+        if eng.arena is not None:
+            eng.arena.close()
+        dist.barrier()
+        dist.destroy_process_group()
+
     if rank != 0:
         if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            _hard_exit()
+            orderly_exit()
         return
 
     # ---------------- roofline of the dominant kernel (fused spatial + reference-KV attention, L0) ----------------
@@ -465,11 +476,13 @@ def main():
                     "note": "window set-up (H2D of window tensors + hoisted projections) charged at 1/40 per step"},
             "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "roofline_conv": roofline_conv, "cpu_baseline": cpu}
+    if world > 1:
+        line["sharded_vs_unsharded_rel_l2"] = shard_err
+        line["sharded_vs_unsharded_note"] = ("final latents of 2 denoising steps, all ranks gathered, against the unsharded "
+                                             "engine on rank 0 (same weights); run-to-run noise of one plan is ~1e-3")
     print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        _hard_exit()
+        orderly_exit()
 
 
 if __name__ == "__main__":

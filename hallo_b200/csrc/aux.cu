@@ -164,23 +164,38 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x1,
         a += sm[y * C + c];
         b += sm[(PY + y) * C + c];
       }
-    atomicAdd(&stats[((long long)n * G + g) * 2 + 0], a);
-    atomicAdd(&stats[((long long)n * G + g) * 2 + 1], b);
+    // partial sums of this pixel chunk: summed in a fixed order by gn_finalize_kernel (no atomics -> bitwise
+    // reproducible, and no memset launch)
+    float* dst = stats + (((long long)n * gridDim.x + blockIdx.x) * G + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
 // per-(frame, channel) scale / shift from the group sums:  y = x * sc + sh
 template <typename T>
-__global__ void gn_finalize_kernel(const float* __restrict__ stats, const T* __restrict__ gamma,
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, int nchunks, const T* __restrict__ gamma,
                                    const T* __restrict__ beta, float eps, int C, int G, int HW,
                                    float* __restrict__ scsh) {
+  __shared__ float gsum[64][2];
   const int n = blockIdx.x;
   const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const float* src = stats + (((long long)n * nchunks + k) * G + g) * 2;
+      a += src[0];
+      b += src[1];
+    }
+    gsum[g][0] = a;
+    gsum[g][1] = b;
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int grp = c / cpg;
     const float cnt = (float)cpg * HW;
-    const float m = stats[((long long)n * G + grp) * 2] / cnt;
-    const float var = fmaxf(stats[((long long)n * G + grp) * 2 + 1] / cnt - m * m, 0.f);
+    const float m = gsum[grp][0] / cnt;
+    const float var = fmaxf(gsum[grp][1] / cnt - m * m, 0.f);
     const float r = rsqrtf(var + eps);
     const float g = Cvt<T>::to_f(gamma[c]);
     scsh[((long long)n * 2) * C + c] = r * g;
@@ -833,7 +848,9 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
     // one-launch path for slabs (HW x C/G halfs) that fit shared memory -- opt-in, see gn_fused_kernel
     const int cpg = C / G;
     const size_t slab = (size_t)HW * cpg * 2;
-    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024 && sc.seg == 0) {
+    // measured (profiles/r2_first_call_summary.txt): the one-launch kernel wins where the three launches are pure
+    // latency (levels 2-3, HW <= 256) and loses at HW >= 1024 (a CTA reads C/G-channel slivers of every pixel)
+    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024 && sc.seg == 0 && HW <= 256) {
       if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
       const int vw = (cpg % 8 == 0) ? 4 : ((cpg % 4 == 0) ? 2 : 1);     // channel pairs per access (16 / 8 / 4 bytes)
       HB_DISPATCH_T(dtype, {
@@ -846,8 +863,7 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
       return HB_OK;
     }
   }
-  HB_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * N * G, s));
-  float* scsh = stats_ws + 2 * (size_t)N * G;          // workspace tail: [N][2][C] scale / shift
+  // workspace: [N][chunks][G][2] partial sums, then [N][2][C] scale / shift
   const int nvec = C / 8;
   if (nvec > 512) return fail(HB_ERR_BAD_SHAPE, "groupnorm: C=%d too wide", C);
   int PY = 256 / nvec;
@@ -856,13 +872,14 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
   int pix_per_cta = 64;                              // >= 2048 CTAs at 64x64x32 frames: enough loads in flight
   if (HW < pix_per_cta) pix_per_cta = HW;
   dim3 g1((HW + pix_per_cta - 1) / pix_per_cta, N);
+  float* scsh = stats_ws + 2 * (size_t)N * G * g1.x;
   const size_t smem = sizeof(float) * 2 * PY * C;
   if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
   HB_DISPATCH_T(dtype, {
     gn_stats_kernel<T><<<g1, threads, smem, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, pix_per_cta, G,
                                                  stats_ws);
     HB_LAUNCH_CHECK();
-    gn_finalize_kernel<T><<<N, 256, 0, s>>>(stats_ws, (const T*)gamma, (const T*)beta, eps, C, G, HW, scsh);
+    gn_finalize_kernel<T><<<N, 256, 0, s>>>(stats_ws, (int)g1.x, (const T*)gamma, (const T*)beta, eps, C, G, HW, scsh);
     HB_LAUNCH_CHECK();
     int ppc = 64;                                     // pixels per CTA of the apply pass
     if (HW < ppc) ppc = HW;

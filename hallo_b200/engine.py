@@ -14,9 +14,13 @@ Layout: every activation is a token matrix [rows, C]; rows are ordered (cfg_half
 i.e. the reference's `(b f) (h w) c` -- so NCHW<->NLC permutes, `rearrange`s and `torch.cat`s of the
 reference disappear (channel concats become two-source reads, frame concats become row offsets).
 
-Multi-GPU: a rank owns `halves` x `frames` (a CFG half and a contiguous frame shard); the only
-exchange on the path is the all-gather of temporal-attention K/V inside a CFG group, plus a tiny
-all-gather of the model output for the CFG combine.
+Multi-GPU: a rank owns a contiguous FRAME group of BOTH CFG halves, so everything except the motion
+modules -- and the CFG combine + DDIM update -- is rank-local and perfectly balanced.  The temporal attention mixes
+all frames of a pixel; around each motion module the ranks swap frame <-> pixel ownership (`_motion_px`): the
+GroupNorm that feeds the module stores its rows straight into the pixel owner's buffer over NVLink, the module runs
+on (all frames x L/R pixels) with a purely local temporal attention and no replicated motion-frame rows, and the
+proj_out GEMM's epilogue stores every row back into the frame owner's buffer.  Two flag barriers per module replace
+the collectives (hallo_b200/peer.py); an NCCL all-to-all variant of the same exchange is kept for A/B runs.
 """
 from __future__ import annotations
 
@@ -36,13 +40,12 @@ class Shard:
     """Which (cfg half, frame) rows this rank owns.  halves: subset of (0, 1); frames: global frame ids."""
     halves: Tuple[int, ...] = (0, 1)
     frames: Tuple[int, ...] = tuple(range(16))
-    group: Optional[object] = None          # torch.distributed group of the ranks sharing a CFG half
+    group: Optional[object] = None          # torch.distributed group of the ranks sharing the window
     group_size: int = 1
-    world: Optional[object] = None          # group for the CFG-combine exchange
-    world_size: int = 1
     rank_in_group: int = 0
-    emulate_group: int = 1                  # profiling aid (bench.py --emulate-shard): pretend this many ranks share
-                                            # the CFG half; the temporal K/V of the peers are copies of the local ones
+    exchange: str = "peer"                  # "peer": kernels store into peer-mapped buffers; "nccl": all_to_all_single
+    emulate_group: int = 1                  # profiling aid (bench.py --emulate-shard): single GPU running ONE rank's
+                                            # shapes of an R-rank job; the peers' rows are copies of the local ones
 
 
 class PackedWeights:
@@ -220,9 +223,48 @@ class DenoiseEngine:
         self.latents = torch.zeros(1, self.cfg.in_channels, self.fl, h, w, dtype=torch.float32, device=self.dev)
         self.model_out: Optional[torch.Tensor] = None
         self.sample: Optional[torch.Tensor] = None      # per-half fp32 sample for the plain forward() API path
-        # opt-in (HALLO_B200_MOTION_A2A=1, sharded runs): frame<->pixel all-to-all around each motion module instead of
-        # the temporal K/V all-gather; untested on hardware in round 1
-        self.motion_a2a = (os.environ.get("HALLO_B200_MOTION_A2A", "0") not in ("", "0")) and self.shard.group_size > 1
+        # frame-sharded window: R ranks (or an emulated R on one GPU) swap frame <-> pixel ownership around motion modules
+        self.R = max(self.shard.group_size, self.shard.emulate_group)
+        self.px = self.R > 1
+        self.arena = None
+        if self.px:
+            assert self.nb == 2, "a frame shard holds both CFG halves (the CFG combine stays rank-local)"
+            assert n_frames % self.R == 0 and self.fl == n_frames // self.R
+            self._init_px()
+
+    # ------------------------------------------------------------------ frame <-> pixel exchange set-up
+    def _motion_modules(self):
+        """(module name, attention name, level, channels) of the executed motion modules, in execution order."""
+        out = []
+        for b in self.W.blocks:
+            lv = self._block_level(b.name)
+            for l in b.layers:
+                if l.motion and l.motion_executed:
+                    out.append((l.motion, l.attn, lv, b.channels))
+        return out
+
+    def _init_px(self):
+        sh, esz = self.shard, torch.empty(0, dtype=self.dtype).element_size()
+        nb, nm, fl, f, R = self.nb, self.nm, self.fl, self.f, self.R
+        regions = []
+        recv = 0
+        for name, _, lv, C in self._motion_modules():
+            L = self.L(lv)
+            if L % R != 0:
+                raise ValueError(f"frame-sharded window: {L} tokens of level {lv} do not split over {R} ranks")
+            regions.append((f"x18.{name}", nb * (nm + f) * (L // R) * C * esz))
+            recv = max(recv, nb * fl * L * C * esz)
+        regions.append(("recv", recv))
+        self.me = sh.rank_in_group
+        if sh.group_size > 1 and sh.exchange == "peer":
+            from .peer import PeerArena
+            self.arena = PeerArena(regions, sh.group, sh.rank_in_group, sh.group_size, self.dev)
+        self._px_regions = dict(regions)
+
+    def _x18(self, name: str, rows: int, C: int) -> torch.Tensor:
+        if self.arena is not None:
+            return self.arena.local(f"x18.{name}", (rows, C), self.dtype)
+        return self.buf(f"x18.{name}", rows, C)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, tag: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
@@ -249,7 +291,8 @@ class DenoiseEngine:
         count and the widest (concatenated) channel count, not a constant."""
         rows = max(self.nb * (self.nm + self.fl), 2 * (1 + self.nm))
         cmax = 2 * max(self.cfg.block_out_channels)
-        return self.buf("gn_ws", 1, 2 * rows * (self.cfg.norm_num_groups + cmax), torch.float32)
+        return self.buf("gn_ws", 1, ops.gn_workspace_floats(rows, self.h * self.w, self.cfg.norm_num_groups, cmax),
+                        torch.float32)
 
     def L(self, level: int) -> int:
         hh, ww = self.level_hw[level]
@@ -265,9 +308,11 @@ class DenoiseEngine:
 
     @torch.no_grad()
     def begin_window(self, *, encoder_hidden_states, audio_embedding, mask_cond_fea, full_mask, face_mask, lip_mask,
-                     motion_scale, banks: Dict[str, torch.Tensor]):
+                     motion_scale, banks: Dict[str, torch.Tensor], local_frames: bool = False):
         """Hoists everything that does not depend on (latents, timestep) -- SURVEY.md 8a "step-invariant work".
-        Inputs use the reference's shapes (full CFG batch, all frames); this rank slices its shard."""
+        Inputs use the reference's shapes (full CFG batch, all frames) and this rank slices its shard; with
+        local_frames=True the per-frame tensors (audio, mask_cond_fea, masks) already hold only this rank's frames
+        (rows ordered (half, local frame)) -- a sharded caller then moves 1/R of them to the device."""
         W, cfg, sh = self.W, self.cfg, self.shard
         dt, dev = self.dtype, self.dev
         halves, frames = list(sh.halves), list(sh.frames)
@@ -285,6 +330,9 @@ class DenoiseEngine:
         self._wset("pe_index_all", torch.arange(nm + f, dtype=torch.int32, device=dev))     # pixel-sharded motion path
 
         ehs = encoder_hidden_states.to(dev, dt)[halves]                       # [nb, 4, 768]
+        if local_frames:
+            assert nb == 2 and audio_embedding.shape[1] == fl and mask_cond_fea.shape[2] == fl
+            fr_idx = torch.arange(fl, device=dev)
         aud = audio_embedding.to(dev, dt)[halves][:, fr_idx]                  # [nb, fl, 32, 768]
         aud2 = aud.reshape(nb * fl * aud.shape[2], aud.shape[3]).contiguous()
         ehs2 = ehs.reshape(nb * ehs.shape[1], ehs.shape[2]).contiguous()
@@ -292,7 +340,7 @@ class DenoiseEngine:
         win["n_aud_tokens"] = aud.shape[2]
         mcf = mask_cond_fea.to(dev, dt)[halves][:, :, fr_idx]                 # [nb, C0, fl, h, w]
         self._wset("mask_cond", mcf.permute(0, 2, 3, 4, 1).reshape(-1, mcf.shape[1]).contiguous())
-        rid = torch.tensor(rows, device=dev)
+        rid = torch.arange(nb * fl, device=dev) if local_frames else torch.tensor(rows, device=dev)
         for nme, m in (("full", full_mask), ("face", face_mask), ("lip", lip_mask)):
             for lv, t in enumerate(m):
                 self._wset(f"mask.{nme}.{lv}", t.to(dev, dt)[rid].reshape(-1).contiguous())
@@ -329,12 +377,26 @@ class DenoiseEngine:
                     # GroupNorm of the motion frames is step-invariant: normalise once into frames [0, nm)
                     tt = f"{l.motion}.temporal_transformer"
                     C = b.channels
-                    gn18 = self.buf(f"{l.motion}.gn18", nb * (nm + fl) * L, C)
                     ws = self._gn_ws()
-                    ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
-                                  n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
-                                  fpb_in=nm, fpb_out=nm + fl, frame_off=0)
+                    if self.px:
+                        # pixel-sharded module: this rank keeps its pixel slice of ALL frames; the motion frames'
+                        # GroupNorm needs whole frames, so it is computed in full once per window and sliced
+                        Lg, F18 = L // self.R, nm + f
+                        gnm = self.buf("mm.gnm", nb * nm * L, C)
+                        ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gnm, ws,
+                                      n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6)
+                        x18 = self._x18(l.motion, nb * F18 * Lg, C)
+                        x18.view(nb, F18, Lg, C)[:, :nm].copy_(
+                            gnm.view(nb, nm, L, C)[:, :, self.me * Lg:(self.me + 1) * Lg])
+                    else:
+                        gn18 = self.buf(f"{l.motion}.gn18", nb * (nm + fl) * L, C)
+                        ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
+                                      n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
+                                      fpb_in=nm, fpb_out=nm + fl, frame_off=0)
         torch.cuda.current_stream().synchronize()
+        if self.arena is not None:
+            import torch.distributed as dist
+            dist.barrier(group=sh.group)        # no rank starts stepping (and storing into peers) before all are set up
 
     def set_schedule(self, timesteps: Sequence[int], coef: torch.Tensor, guidance: float):
         """Per-window schedule.  The tables keep their device addresses (a captured graph reads them); the step count
@@ -465,66 +527,51 @@ class DenoiseEngine:
         ops.gemm(h3, W[f"{name}.proj_out.w"], out, bias=W[f"{name}.proj_out.b"], residual=x)
         return out
 
-    def _gather_kv(self, qkv, C, L):
-        """Temporal K/V of all frames of this CFG half.  Single rank per half: a view.  Sharded: the one
-        NCCL all-gather on the path -- motion-frame rows are replicated, so only the local
-        frames' K/V are exchanged."""
-        sh = self.shard
-        nb, nm, fl = self.nb, self.nm, self.fl
-        Fl = nm + fl
-        if sh.group_size == 1 and sh.emulate_group > 1:
-            # single-GPU stand-in for a rank of a sharded job: same buffers, same temporal-attention shape (Fk keys),
-            # device-local copies instead of the NCCL all-gather
-            assert nb == 1
-            g = sh.emulate_group
-            Fk = nm + fl * g
-            src = qkv.view(Fl, L, 3 * C)
-            full = self.buf("mm.kvfull", Fk * L, 2 * C)
-            fv = full.view(Fk, L, 2 * C)
-            fv[:nm].copy_(src[:nm, :, C:])
-            for r in range(g):
-                fv[nm + r * fl: nm + (r + 1) * fl].copy_(src[nm:, :, C:])
-            return full[:, :C], full[:, C:], Fk
-        if sh.group_size == 1:
-            return qkv[:, C:2 * C], qkv[:, 2 * C:], Fl
-        import torch.distributed as dist
-        assert nb == 1
-        Fk = nm + fl * sh.group_size
-        with ops.timed_region(f"kv_allgather_pack C{C} L{L}"):
-            loc = qkv.view(Fl, L, 3 * C)[nm:, :, C:].contiguous()                 # [fl, L, 2C]
-            full = self.buf("mm.kvfull", Fk * L, 2 * C)
-            full.view(Fk, L, 2 * C)[:nm].copy_(qkv.view(Fl, L, 3 * C)[:nm, :, C:])
-        with ops.timed_region(f"kv_allgather_nccl C{C} L{L} G{sh.group_size}"):
-            dist.all_gather_into_tensor(full.view(Fk, L, 2 * C)[nm:].reshape(-1), loc.reshape(-1), group=sh.group)
-        return full[:, :C], full[:, C:], Fk
+    def _motion_px(self, name: str, x, level: int, C: int, out_tag: str):
+        """Motion module of a frame-sharded window (motion_module.py:270-316 + :387-423): frame <-> pixel ownership is
+        swapped around the module.  Rank `me` owns frames [me*fl, (me+1)*fl) everywhere else; inside the module it owns
+        the pixel slice [me*Lg, (me+1)*Lg) of ALL nm + f frames (x18 rows: (half, frame, pixel)).
 
-    def _motion_a2a(self, name: str, x, level: int, C: int, out_tag: str):
-        """Motion module with frame<->pixel ownership swapped around it (SURVEY.md 8e "alternative"): every rank of the
-        CFG group normalises its own frames (GroupNorm needs whole frames), an all-to-all hands each rank the pixel slice
-        [me*L/G, (me+1)*L/G) of ALL frames, the module (proj_in .. proj_out, temporal attention over the nm + f frames)
-        runs on that slice with no replicated motion-frame work and no K/V exchange, and a second all-to-all returns the
-        rows to their frame owners, which add the residual.  Exchanged bytes: 2 * (G-1)/G * fl*L*C*2 per module instead
-        of 2 * (G-1) * fl*L*2C*2 for the two K/V all-gathers."""
+          in : GroupNorm of the local frames; its apply pass stores each row into the pixel owner's x18 over NVLink
+               (ops.groupnorm_scatter) -> flag barrier
+          mid: proj_in, 2 x {LN + PE, QKV, temporal attention over the nm + f frames, to_out}, FF -- all rank-local,
+               no replicated motion-frame rows
+          out: proj_out GEMM whose epilogue stores every (frame, pixel) row into the frame owner's `recv`
+               (hb_row_scatter) -> flag barrier -> out = recv + x (the module's residual)
+
+        exchange == "nccl" performs the same two swaps with all_to_all_single (A/B baseline); emulate_group fills the
+        peers' rows with copies of the local ones (single-GPU profile of one rank's shapes)."""
         W, win, H, sh = self.W, self.window, self.cfg.heads, self.shard
-        nm, fl, gs, me = self.nm, self.fl, sh.group_size, sh.rank_in_group
-        assert self.nb == 1
+        nb, nm, fl, f, R, me = self.nb, self.nm, self.fl, self.f, self.R, self.me
         L = self.L(level)
-        assert L % gs == 0, "pixel-sharded motion path needs L divisible by the group size"
-        Lg, F = L // gs, fl * gs
-        F18 = nm + F
-        M18 = F18 * Lg
+        Lg, F18 = L // R, nm + f
+        M18 = nb * F18 * Lg
         tt = f"{name}.temporal_transformer"
         tb = f"{tt}.transformer_blocks.0"
-        # GroupNorm of the local frames (frame-major rows), then scatter pixel slices to their owners
-        gnl = self.buf("mm.gnl", fl * L, C)
-        self._gn(x, f"{tt}.norm", gnl, fl, L, 1e-6, False)
-        from .dist import frames_to_pixels, pixels_to_frames
-        send = self.buf("mm.a2a.s", gs * fl * Lg, C)
-        x18 = self.buf("mm.x18", M18, C)
-        gn18 = self.buf(f"{name}.gn18", (nm + fl) * L, C)              # rows of frames [0, nm): begin_window
-        x18.view(F18, Lg, C)[:nm].copy_(gn18.view(nm + fl, L, C)[:nm, me * Lg:(me + 1) * Lg])
-        with ops.timed_region(f"a2a_frames_to_pixels C{C} L{L} G{gs}"):
-            frames_to_pixels(gnl, send, x18[nm * Lg:], fl, gs, sh.group)   # chunk r = frames of rank r, my pixels
+        x18 = self._x18(name, M18, C)
+        ws = self._gn_ws()
+        esz = x.element_size()
+        if self.arena is not None:
+            ops.groupnorm_scatter(x, W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], self.arena.addrs(f"x18.{name}"), ws,
+                                  n_frames=nb * fl, hw=L, groups=self.cfg.norm_num_groups, eps=1e-6, fpb_in=fl,
+                                  fpb_out=F18, frame_off=nm + me * fl)
+            with ops.timed_region(f"peer_barrier in C{C} L{L}"):
+                self.arena.barrier()
+        else:
+            gnl = self.buf("mm.gnl", nb * fl * L, C)
+            self._gn(x, f"{tt}.norm", gnl, nb * fl, L, 1e-6, False)
+            g5 = gnl.view(nb, fl, R, Lg, C)
+            x5 = x18.view(nb, F18, Lg, C)
+            if sh.group_size > 1:
+                import torch.distributed as dist
+                send = self.buf("mm.a2a.s", R * nb * fl * Lg, C)
+                recv = self.buf("mm.a2a.r", R * nb * fl * Lg, C)
+                send.view(R, nb, fl, Lg, C).copy_(g5.permute(2, 0, 1, 3, 4))            # chunk d = my frames, pixel slice d
+                with ops.timed_region(f"a2a_frames_to_pixels C{C} L{L} R{R}"):
+                    dist.all_to_all_single(recv, send, group=sh.group)                 # chunk s = frames of rank s, my slice
+                x5[:, nm:].view(nb, R, fl, Lg, C).copy_(recv.view(R, nb, fl, Lg, C).permute(1, 0, 2, 3, 4))
+            else:                                                                      # emulation: peers = copies of me
+                x5[:, nm:].view(nb, R, fl, Lg, C).copy_(g5[:, :, me].unsqueeze(1).expand(nb, R, fl, Lg, C))
         h = self.buf("mm.h", M18, C)
         ops.gemm(x18, W[f"{tt}.proj_in.w"], h, bias=W[f"{tt}.proj_in.b"])
         for a in range(2):
@@ -533,24 +580,47 @@ class DenoiseEngine:
             qkv = self.buf("mm.qkv", M18, 3 * C)
             ops.gemm(n, W[f"{tb}.attention_blocks.{a}.qkv"], qkv)
             o = self.buf("mm.attn", M18, C)
-            ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, batch=1, fq=F18, fk=F18, tokens=Lg,
+            ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, batch=nb, fq=F18, fk=F18, tokens=Lg,
                                    heads=H)
             h2 = self.buf(f"mm.h{a + 1}", M18, C)
             ops.gemm(o, W[f"{tb}.attention_blocks.{a}.to_out.0.w"], h2,
                      bias=W[f"{tb}.attention_blocks.{a}.to_out.0.b"], residual=h)
             h = h2
         h = self._ff(h, f"{tb}.ff", f"{tb}.ff_norm", "mm.h3")
-        y = self.buf("mm.y", F * Lg, C)                                # real frames only, global frame order
-        ops.gemm(h[nm * Lg:], W[f"{tt}.proj_out.w"], y, bias=W[f"{tt}.proj_out.b"])
-        recv = self.buf("mm.a2a.r", gs * fl * Lg, C)
-        out = self.buf(out_tag, fl * L, C)
-        with ops.timed_region(f"a2a_pixels_to_frames C{C} L{L} G{gs}"):
-            pixels_to_frames(y, recv, x, out, fl, gs, sh.group)        # chunk g = my frames, pixel slice g; + residual
+        out = self.buf(out_tag, nb * fl * L, C)
+        if self.arena is not None:
+            recv = self.arena.local("recv", (nb * fl * L, C), self.dtype)
+            bases = self.arena.addrs("recv")
+            for b in range(nb):                          # real frames only (the caller drops the motion frames)
+                rows_in = h[(b * F18 + nm) * Lg:(b + 1) * F18 * Lg]                    # row r = g * Lg + p, g global frame
+                sc = ops.row_scatter(bases, seg=Lg, segs_per_dest=fl, seg_stride=L, row0=b * fl * L + me * Lg)
+                ops.gemm(rows_in, W[f"{tt}.proj_out.w"], recv[:f * Lg], bias=W[f"{tt}.proj_out.b"], scatter=sc)
+            with ops.timed_region(f"peer_barrier out C{C} L{L}"):
+                self.arena.barrier()
+            ops.add(recv, x, out)
+        else:
+            y = self.buf("mm.y", nb * f * Lg, C)
+            for b in range(nb):
+                ops.gemm(h[(b * F18 + nm) * Lg:(b + 1) * F18 * Lg], W[f"{tt}.proj_out.w"], y[b * f * Lg:(b + 1) * f * Lg],
+                         bias=W[f"{tt}.proj_out.b"])
+            y5 = y.view(nb, R, fl, Lg, C)
+            if sh.group_size > 1:
+                import torch.distributed as dist
+                send = self.buf("mm.a2a.s", R * nb * fl * Lg, C)
+                recv = self.buf("mm.a2a.r", R * nb * fl * Lg, C)
+                send.view(R, nb, fl, Lg, C).copy_(y5.permute(1, 0, 2, 3, 4))            # chunk d = frames of rank d, my slice
+                with ops.timed_region(f"a2a_pixels_to_frames C{C} L{L} R{R}"):
+                    dist.all_to_all_single(recv, send, group=sh.group)                 # chunk s = my frames, pixel slice s
+                torch.add(recv.view(R, nb, fl, Lg, C).permute(1, 2, 0, 3, 4), x.view(nb, fl, R, Lg, C),
+                          out=out.view(nb, fl, R, Lg, C))
+            else:
+                mine = y5[:, me].unsqueeze(2).expand(nb, fl, R, Lg, C)                  # emulation: every slice = mine
+                torch.add(mine, x.view(nb, fl, R, Lg, C), out=out.view(nb, fl, R, Lg, C))
         return out
 
     def _motion(self, name: str, attn_name: str, x, level: int, C: int, out_tag: str):
-        if self.motion_a2a:
-            return self._motion_a2a(name, x, level, C, out_tag)
+        if self.px:
+            return self._motion_px(name, x, level, C, out_tag)
         W, win, H = self.W, self.window, self.cfg.heads
         nb, nm, fl = self.nb, self.nm, self.fl
         Fl = nm + fl
@@ -567,9 +637,8 @@ class DenoiseEngine:
                          tokens_per_frame=L, frames=Fl)
             qkv = self.buf("mm.qkv", Mm, 3 * C)
             ops.gemm(n, W[f"{tb}.attention_blocks.{a}.qkv"], qkv)
-            k, v, Fk = self._gather_kv(qkv, C, L)
             o = self.buf("mm.attn", Mm, C)
-            ops.temporal_attention(qkv[:, :C], k, v, o, batch=nb, fq=Fl, fk=Fk, tokens=L, heads=H)
+            ops.temporal_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, batch=nb, fq=Fl, fk=Fl, tokens=L, heads=H)
             h2 = self.buf(f"mm.h{a + 1}", Mm, C)
             ops.gemm(o, W[f"{tb}.attention_blocks.{a}.to_out.0.w"], h2,
                      bias=W[f"{tb}.attention_blocks.{a}.to_out.0.b"], residual=h)
@@ -666,29 +735,7 @@ class DenoiseEngine:
     @torch.no_grad()
     def _step_tail(self):
         """CFG combine + DDIM update + step counter (face_animate.py:415-420)."""
-        sh = self.shard
-        mo = self.model_out
-        if self.nb == 1 and sh.world_size == 1:
-            # profiling aid (bench.py --emulate-shard): one rank's workload without its peer; the combine sees the same
-            # half twice, which keeps the kernel sequence and shapes of a real rank
-            n = mo.shape[0]
-            both = self.buf("out.both", 2 * n, mo.shape[1])
-            both[:n].copy_(mo)
-            both[n:].copy_(mo)
-            mo = both
-        elif self.nb == 1:
-            # the two CFG halves live on different ranks: exchange the (tiny) model outputs
-            import torch.distributed as dist
-            allm = self.buf("out.all", sh.world_size * mo.shape[0], mo.shape[1])
-            with ops.timed_region("cfg_exchange_nccl"):
-                dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1), group=sh.world)
-            gs = sh.group_size
-            me = sh.rank_in_group
-            n = mo.shape[0]
-            both = self.buf("out.both", 2 * n, mo.shape[1])
-            both[:n].copy_(allm[me * n:(me + 1) * n])                         # uncond group = ranks [0, gs)
-            both[n:].copy_(allm[(gs + me) * n:(gs + me + 1) * n])             # cond group = ranks [gs, 2gs)
-            mo = both
+        mo = self.model_out                    # both CFG halves of the local frames: the combine is rank-local
         ops.cfg_ddim_step(mo, self.latents, self.coef, self.step_idx, guidance=self.guidance)
         ops.advance_step(self.step_idx, self.n_steps)
 

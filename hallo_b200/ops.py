@@ -67,8 +67,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
          group_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0, alpha: float = 1.0,
          geglu: bool = False, silu: bool = False, a2: Optional[torch.Tensor] = None,
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
-         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M, N(/2)] = epilogue(cat([a, a2], 1) @ w.T); see include/hallo_b200.h."""
+         stats_out: Optional[torch.Tensor] = None, scatter: Optional["lib.RowScatter"] = None) -> torch.Tensor:
+    """out[M, N(/2)] = epilogue(cat([a, a2], 1) @ w.T); see include/hallo_b200.h.  With `scatter` (row_scatter()) the
+    rows go to the per-destination buffers instead of `out` (which then only supplies ldc / the shape check)."""
     p = lib.GemmParams()
     p.dtype = lib.dtype_code(a.dtype)
     M, K1 = a.shape
@@ -98,8 +99,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.numel() >= 2 * M and stats_out.is_contiguous()
         p.stats_out = lib.ptr(stats_out)
+    if scatter is not None:
+        assert residual is None
+        p.scatter = C.addressof(scatter)
     lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "gemm")
     return out
+
+
+def row_scatter(bases, seg: int, segs_per_dest: int, seg_stride: int, row0: int) -> "lib.RowScatter":
+    """hb_row_scatter: GEMM output row r -> bases[(r // seg) // segs_per_dest] at row
+    ((r // seg) % segs_per_dest) * seg_stride + row0 + r % seg."""
+    sc = lib.RowScatter()
+    assert 1 <= len(bases) <= 16
+    for i, b in enumerate(bases):
+        sc.base[i] = int(b)
+    sc.seg, sc.segs_per_dest, sc.seg_stride, sc.row0 = int(seg), int(segs_per_dest), int(seg_stride), int(row0)
+    return sc
 
 
 @_timed(lambda x, w, out, **kw: f"conv3x3 n{x.shape[0]} {x.shape[1]}x{x.shape[2]} {x.shape[3]}->{w.shape[0]}")
@@ -189,6 +204,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
     return out
 
 
+def gn_workspace_floats(n_frames: int, hw: int, groups: int, channels: int) -> int:
+    """fp32 elements hallo_b200_groupnorm needs: per-chunk (64 pixels) group sums + per-channel scale / shift."""
+    return 2 * n_frames * (groups * ((hw + 63) // 64) + channels)
+
+
 @_timed(lambda x1, *a, **kw: f"groupnorm C{x1.shape[1] + (0 if kw.get('x2') is None else kw['x2'].shape[1])} rows{x1.shape[0]}")
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, stats_ws: torch.Tensor, *,
               n_frames: int, hw: int, groups: int = 32, eps: float = 1e-5, silu: bool = False,
@@ -197,12 +217,36 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: to
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous()) and out.is_contiguous()
     C1 = x1.shape[1]
     C2 = 0 if x2 is None else x2.shape[1]
-    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= 2 * n_frames * (groups + C1 + C2)
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= gn_workspace_floats(n_frames, hw, groups, C1 + C2)
     lib.check(lib.load().hallo_b200_groupnorm(
         _i(lib.dtype_code(x1.dtype)), C.c_void_p(lib.ptr(x1)), _i(C1), C.c_void_p(lib.ptr(x2)), _i(C2), _i(n_frames),
         _i(hw), _i(groups), C.c_void_p(lib.ptr(gamma)), C.c_void_p(lib.ptr(beta)), C.c_float(eps), _i(1 if silu else 0),
         C.c_void_p(lib.ptr(out)), C.c_void_p(lib.ptr(stats_ws)), _i(fpb_in), _i(fpb_out), _i(frame_off),
         lib.current_stream()), "groupnorm")
+    return out
+
+
+@_timed(lambda x1, *a, **kw: f"groupnorm_scatter C{x1.shape[1]} rows{x1.shape[0]}")
+def groupnorm_scatter(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_addrs, stats_ws: torch.Tensor, *,
+                      n_frames: int, hw: int, groups: int = 32, eps: float = 1e-5, fpb_in: int = 0, fpb_out: int = 0,
+                      frame_off: int = 0) -> None:
+    """GroupNorm whose rows are stored by pixel slice into `out_addrs` (one device address per destination rank):
+    pixel p of output frame n_out -> out_addrs[p // seg] + ((n_out * seg + p % seg) * C), seg = hw // len(out_addrs)."""
+    assert x1.is_contiguous() and hw % len(out_addrs) == 0
+    C1 = x1.shape[1]
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= gn_workspace_floats(n_frames, hw, groups, C1)
+    arr = (C.c_void_p * len(out_addrs))(*[C.c_void_p(int(a)) for a in out_addrs])
+    lib.check(lib.load().hallo_b200_groupnorm_scatter(
+        _i(lib.dtype_code(x1.dtype)), C.c_void_p(lib.ptr(x1)), _i(C1), _i(n_frames), _i(hw), _i(groups),
+        C.c_void_p(lib.ptr(gamma)), C.c_void_p(lib.ptr(beta)), C.c_float(eps), arr, _i(len(out_addrs)),
+        C.c_void_p(lib.ptr(stats_ws)), _i(fpb_in), _i(fpb_out), _i(frame_off), lib.current_stream()), "groupnorm_scatter")
+
+
+@_timed(lambda a, *r, **kw: f"add n{a.numel()}")
+def add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous() and a.numel() == b.numel() == out.numel()
+    lib.check(lib.load().hallo_b200_add(_i(lib.dtype_code(a.dtype)), C.c_void_p(lib.ptr(a)), C.c_void_p(lib.ptr(b)),
+                                        C.c_void_p(lib.ptr(out)), C.c_int64(a.numel()), lib.current_stream()), "add")
     return out
 
 

@@ -56,7 +56,7 @@ int64_t hallo_b200_launch_count(int reset);
  *   "gemm_tepi"   GEMM / conv epilogue staged through shared memory and written by TMA stores        (default 1)
  *   "gemm_1cta"   force the single-CTA GEMM kernel                                                    (default 0)
  *   "gemm_fill"   narrower GEMM N tiles (128 / 64) when the widest tile would leave SMs idle          (default 1)
- *   "attn_occ2"   head_dim 40: 64-key steps and two CTAs (four query tiles) per SM                    (default 0)
+ *   "attn_occ2"   head_dim 40: 64-key steps and two CTAs (four query tiles) per SM                    (default 1)
  *   "attn_poly"   n: every n-th exponential on the FMA pipe (2..4), 0 = all on the SFU               (default 0)
  *   "attn_v1"     force the single-tile attention kernel                                              (default 0)
  *   "xattn_tc"    tcgen05 cross-attention (0: CUDA-core kernel)                                       (default 1)
@@ -201,7 +201,8 @@ int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void* out, int64
 /* Per-frame GroupNorm over channels-last frames [N, HW, C1(+C2)] (InflatedGroupNorm, resnet.py:88-101;
  * transformer_3d.py:197; motion_module.py:290), optional SiLU (resnet.py:386-387, 399).
  * x2/C2: second channel-concatenated source (UNet skip connection) or NULL/0.
- * stats_ws: fp32 workspace of N*G*2 + N*2*(C1+C2) floats (group sums, then per-channel scale/shift).  Output frame n -> (n / fpb_in) * fpb_out + frame_off + n % fpb_in
+ * stats_ws: fp32 workspace of N*ceil(HW/64)*G*2 + N*2*(C1+C2) floats (per-chunk group sums -- summed in a fixed order, no
+ * atomics: results are bitwise reproducible -- then per-channel scale/shift).  Output frame n -> (n / fpb_in) * fpb_out + frame_off + n % fpb_in
  * (fpb_in <= 0: identity) -- used to drop frames into the 18-frame temporal buffer. */
 int hallo_b200_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, int N, int HW, int G,
                          const void* gamma, const void* beta, float eps, int silu, void* out,

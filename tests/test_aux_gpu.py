@@ -69,7 +69,7 @@ def test_groupnorm(C1, C2, hw, silu):
     gam = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, DT)
     bet = (0.1 * torch.randn(C, generator=g)).to(dev, DT)
     out = torch.empty(n * hw, C, device=dev, dtype=DT)
-    ws = torch.empty(2 * n * (32 + C), device=dev, dtype=torch.float32)
+    ws = torch.empty(ops.gn_workspace_floats(n, hw, 32, C), device=dev, dtype=torch.float32)
     ops.groupnorm(x1, gam, bet, out, ws, n_frames=n, hw=hw, eps=1e-5, silu=silu, x2=x2)
     torch.cuda.synchronize()
     xc = x1 if x2 is None else torch.cat([x1, x2], 1)
@@ -81,6 +81,63 @@ def test_groupnorm(C1, C2, hw, silu):
     assert rel_l2(out, ref) < 2e-3
 
 
+def test_groupnorm_scatter_single_destination_and_slices():
+    """hallo_b200_groupnorm_scatter (the frame -> pixel swap in front of a motion module, fused into the GroupNorm's
+    store): with every destination pointing into ONE local buffer at different offsets the result must be the plain
+    GroupNorm rearranged as [dest][frame_out][pixel slice] -- the addressing the peer-memory path relies on."""
+    from hallo_b200 import ops
+    dev = _dev()
+    nb, fl, hw, C, R, nm, me = 2, 2, 64, 320, 4, 2, 1
+    f, seg = fl * R, hw // R
+    F18 = nm + f
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(nb * fl * hw, C, generator=g).to(dev, DT)
+    gam = (1 + 0.1 * torch.randn(C, generator=g)).to(dev, DT)
+    bet = (0.1 * torch.randn(C, generator=g)).to(dev, DT)
+    dest = torch.zeros(R, nb * F18 * seg, C, device=dev, dtype=DT)        # "rank d's x18 buffer"
+    ws = torch.empty(ops.gn_workspace_floats(nb * fl, hw, 32, C), device=dev, dtype=torch.float32)
+    ops.groupnorm_scatter(x, gam, bet, [dest[d].data_ptr() for d in range(R)], ws, n_frames=nb * fl, hw=hw, eps=1e-6,
+                          fpb_in=fl, fpb_out=F18, frame_off=nm + me * fl)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().view(nb * fl, hw, C).permute(0, 2, 1), 32, gam.float(), bet.float(), 1e-6).permute(0, 2, 1)
+    ref = ref.reshape(nb, fl, R, seg, C)
+    d5 = dest.view(R, nb, F18, seg, C)
+    got = d5[:, :, nm + me * fl: nm + (me + 1) * fl].permute(1, 2, 0, 3, 4)          # [nb, fl, R, seg, C]
+    assert rel_l2(got, ref) < 2e-3
+    untouched = torch.cat([d5[:, :, :nm + me * fl].reshape(-1), d5[:, :, nm + (me + 1) * fl:].reshape(-1)])
+    assert float(untouched.abs().max()) == 0.0
+
+
+def test_gemm_row_scatter_and_add():
+    """hb_row_scatter epilogue (a motion module's proj_out storing rows into the frame owners' buffers) and
+    hallo_b200_add, on one device: destinations are slices of a local buffer."""
+    from hallo_b200 import ops
+    dev = _dev()
+    nb, fl, R, Lg, C, me = 2, 2, 4, 32, 320, 2
+    f, L = fl * R, Lg * R
+    g = torch.Generator().manual_seed(22)
+    a = torch.randn(f * Lg, C, generator=g).to(dev, DT)                    # rows (global frame g, pixel p of my slice)
+    w = (torch.randn(C, C, generator=g) * 0.05).to(dev, DT)
+    bias = torch.randn(C, generator=g).to(dev, DT)
+    recv = torch.zeros(R, nb * fl * L, C, device=dev, dtype=DT)            # "rank d's recv buffer"
+    b = 1
+    sc = ops.row_scatter([recv[d].data_ptr() for d in range(R)], seg=Lg, segs_per_dest=fl, seg_stride=L,
+                         row0=b * fl * L + me * Lg)
+    ops.gemm(a, w, recv[0][:f * Lg], bias=bias, scatter=sc)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t() + bias.float()).view(R, fl, Lg, C)   # [dest, local frame, pixel, C]
+    got = recv.view(R, nb, fl, R, Lg, C)[:, b, :, me]
+    assert rel_l2(got, ref) < 2e-3
+    mask = torch.ones_like(recv.view(R, nb, fl, R, Lg, C), dtype=torch.bool)
+    mask[:, b, :, me] = False
+    assert float(recv.view(R, nb, fl, R, Lg, C)[mask].abs().max()) == 0.0
+    x = torch.randn(nb * fl * L, C, generator=g).to(dev, DT)
+    out = torch.empty_like(x)
+    ops.add(recv[0], x, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, (recv[0].float() + x.float()).to(DT))
+
+
 def test_groupnorm_frame_remap():
     from hallo_b200 import ops
     dev = _dev()
@@ -90,7 +147,7 @@ def test_groupnorm_frame_remap():
     gam = torch.ones(C, device=dev, dtype=DT)
     bet = torch.zeros(C, device=dev, dtype=DT)
     out = torch.zeros(b * (f + 2) * hw, C, device=dev, dtype=DT)
-    ws = torch.empty(2 * b * f * (32 + C), device=dev, dtype=torch.float32)
+    ws = torch.empty(ops.gn_workspace_floats(b * f, hw, 32, C), device=dev, dtype=torch.float32)
     ops.groupnorm(x, gam, bet, out, ws, n_frames=b * f, hw=hw, eps=1e-6, fpb_in=f, fpb_out=f + 2, frame_off=2)
     torch.cuda.synchronize()
     ref = F.group_norm(x.float().view(b * f, hw, C).permute(0, 2, 1), 32, None, None, 1e-6).permute(0, 2, 1)

@@ -56,7 +56,7 @@ def test_kernel_selection_options_roundtrip():
     import __graft_entry__ as g
     g.build()
     from hallo_b200 import lib
-    defaults = {"gemm_tepi": 1, "gemm_1cta": 0, "gemm_fill": 1, "attn_occ2": 0, "attn_poly": 0, "attn_v1": 0,
+    defaults = {"gemm_tepi": 1, "gemm_1cta": 0, "gemm_fill": 1, "attn_occ2": 1, "attn_poly": 0, "attn_v1": 0,
                 "xattn_tc": 1, "tattn_mma": 1, "gn_fused": 1}
     for name, dflt in defaults.items():
         if os.environ.get("HALLO_B200_" + name.upper()) is None:
@@ -123,59 +123,66 @@ def test_scheduler_tables():
 
 def test_shard_layout():
     from hallo_b200.dist import shard_layout
-    for world in (1, 2, 4, 8):
+    for world in (1, 2, 4, 8, 16):
         lay = shard_layout(world, 16)
         rows = sorted((b, g) for halves, frames in lay for b in halves for g in frames)
         assert rows == [(b, g) for b in (0, 1) for g in range(16)]    # every (half, frame) owned exactly once
+        assert all(halves == (0, 1) and len(frames) == 16 // world for halves, frames in lay)   # balanced, CFG-local
     with pytest.raises(ValueError):
         shard_layout(3, 16)
+
+
+def test_row_scatter_matches_the_frame_owner_layout():
+    """The proj_out epilogue's hb_row_scatter parameters (engine._motion_px): GEMM row (global frame g, pixel p of rank
+    me's slice) of half b must land at row (b*fl + g % fl)*L + me*Lg + p of rank g // fl; the GroupNorm scatter's
+    (frame n = b*fl + j, pixel p) at row (b*F18 + nm + me*fl + j)*Lg + p % Lg of rank p // Lg."""
+    from hallo_b200.dist import scatter_row_destination
+    nb, nm, f, R, L = 2, 2, 16, 4, 64
+    fl, Lg, F18 = f // R, L // R, nm + f
+    for me in range(R):
+        for b in range(nb):
+            for g in range(f):
+                for pp in (0, 1, Lg - 1):
+                    d, row = scatter_row_destination(g * Lg + pp, seg=Lg, segs_per_dest=fl, seg_stride=L,
+                                                     row0=b * fl * L + me * Lg)
+                    assert d == g // fl and row == (b * fl + g % fl) * L + me * Lg + pp
+    # GroupNorm scatter (csrc/aux.cu gn_apply_kernel): n_out = (n // fpb_in) * fpb_out + frame_off + n % fpb_in
+    for me in range(R):
+        for n in range(nb * fl):
+            n_out = (n // fl) * F18 + (nm + me * fl) + n % fl
+            b, j = divmod(n, fl)
+            assert n_out == b * F18 + nm + me * fl + j
 
 
 WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["HB_ROOT"])
-from hallo_b200.dist import plan_shard, gather_temporal_kv, frames_to_pixels, pixels_to_frames
+from hallo_b200.dist import plan_shard, frames_to_pixels, pixels_to_frames
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-n_frames, nm, L, C2 = 8, 2, 3, 4
-# 4 "virtual" ranks cannot run here; world=2 => one rank per CFG half, group_size 1: the gather degenerates.
-sh = plan_shard(rank, world, n_frames)
-assert sh.halves == (rank,) and sh.frames == tuple(range(n_frames)) and sh.group_size == 1
-# exercise the gather collective itself with a 2-rank frame group (the code path ranks of one CFG half use)
-g = dist.new_group([0, 1])
-fl = n_frames // 2
-glob = torch.arange((nm + n_frames) * L * C2, dtype=torch.float32).reshape(nm + n_frames, L, C2)
-local = glob[nm + rank * fl: nm + (rank + 1) * fl]
-full = gather_temporal_kv(local, glob[:nm], g, 2)
-assert torch.equal(full, glob), (rank, full.flatten()[:8])
-# CFG-combine exchange layout (engine._step_tail): all_gather over world, uncond group first
-mo = torch.full((5, 8), float(rank))
-allm = torch.empty(world * 5, 8)
-dist.all_gather_into_tensor(allm.view(-1), mo.reshape(-1))
-assert float(allm[:5].mean()) == 0.0 and float(allm[5:].mean()) == 1.0
-# frame<->pixel exchange around a motion module (engine._motion_a2a): a per-pixel op that mixes ALL frames (here a
-# cumulative sum over the frame axis + a per-frame scale) computed on pixel slices must equal the unsharded result
-Lp, Cc = 6, 4
-xg = torch.arange(n_frames * Lp * Cc, dtype=torch.float32).reshape(n_frames, Lp, Cc) / 7.0      # all frames (global)
-x_loc = xg[rank * fl:(rank + 1) * fl].contiguous()                                               # my frames
-Lg = Lp // 2
-send = torch.empty(2 * fl * Lg, Cc)
-allf = torch.empty(2 * fl * Lg, Cc)
-frames_to_pixels(x_loc.reshape(fl * Lp, Cc), send, allf, fl, 2, g)
-assert torch.equal(allf.view(n_frames, Lg, Cc), xg[:, rank * Lg:(rank + 1) * Lg]), rank     # my pixel slice of all frames
-scale = torch.arange(1, n_frames + 1, dtype=torch.float32).view(n_frames, 1, 1)
-y = (allf.view(n_frames, Lg, Cc).cumsum(0) * scale).reshape(n_frames * Lg, Cc).contiguous()
-recv = torch.empty_like(y)
-out = torch.empty(fl * Lp, Cc)
-pixels_to_frames(y, recv, x_loc.reshape(fl * Lp, Cc), out, fl, 2, g)
-ref = (xg.cumsum(0) * scale + xg)[rank * fl:(rank + 1) * fl]
-assert torch.allclose(out.view(fl, Lp, Cc), ref), rank
+n_frames, nb = 8, 2
+sh = plan_shard(rank, world, n_frames, exchange="nccl")
+fl = n_frames // world
+assert sh.halves == (0, 1) and sh.frames == tuple(range(rank * fl, (rank + 1) * fl)) and sh.group_size == world
+# frame<->pixel exchange around a motion module (engine._motion_px): a per-pixel op that mixes ALL frames (a cumulative
+# sum over the frame axis + a per-frame scale) computed on pixel slices must equal the unsharded result, both halves
+L, C = 6, 4
+xg = (torch.arange(nb * n_frames * L * C, dtype=torch.float32).reshape(nb, n_frames, L, C) / 7.0).sin()   # global
+x_loc = xg[:, rank * fl:(rank + 1) * fl].contiguous()                                   # my frames, both halves
+Lg = L // world
+allf = frames_to_pixels(x_loc, nb, fl, world, sh.group)
+assert torch.equal(allf, xg[:, :, rank * Lg:(rank + 1) * Lg]), rank                      # my pixel slice of all frames
+scale = torch.arange(1, n_frames + 1, dtype=torch.float32).view(1, n_frames, 1, 1)
+y = (allf.cumsum(1) * scale).contiguous()
+back = pixels_to_frames(y, nb, fl, world, sh.group) + x_loc
+ref = (xg.cumsum(1) * scale + xg)[:, rank * fl:(rank + 1) * fl]
+assert torch.allclose(back, ref), rank
 dist.destroy_process_group()
 print("ok", rank)
 '''
 
 
-def test_gloo_world2_temporal_gather(tmp_path):
+def test_gloo_world2_frame_pixel_exchange(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(WORKER)
     env = dict(os.environ, HB_ROOT=ROOT, MASTER_ADDR="127.0.0.1")

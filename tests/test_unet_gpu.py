@@ -97,6 +97,43 @@ def test_unet_forward_run_to_run_reproducibility(model):
     assert err < 2e-3
 
 
+def test_pixel_transposed_motion_modules_on_one_gpu(model):
+    """The frame-sharded path (engine._motion_px: frame <-> pixel swap around every motion module) without a second GPU:
+    with a window whose frames repeat with period fl, the rows the other ranks would send are copies of the local ones,
+    which is exactly what Shard(emulate_group=R) substitutes -- so rank 0's emulated shard must reproduce frames
+    [0, fl) of the unsharded forward.  Checks the x18 layout, the positional-encoding indices, the local-frame window
+    slicing and the CFG-local step tail; the peer-memory transport itself is tests/test_multigpu_gpu.py."""
+    from hallo_b200.dist import window_inputs_to_device
+    from hallo_b200.engine import DenoiseEngine, Shard
+    from hallo_b200.spec import UNetConfig
+    from hallo_b200.synth import synth_inputs
+    m, _ = model
+    dev = _dev()
+    f, R, size = 16, 4, 32
+    fl = f // R
+    inp = synth_inputs(UNetConfig(), size, size, f, seed=31, timestep=600, motion_scale=(1.0, 0.8, 1.2))
+    per = lambda t, dim: t.index_select(dim, torch.arange(f) % fl)          # frames repeat with period fl
+    inp["sample"] = per(inp["sample"], 2)
+    inp["audio_embedding"] = per(inp["audio_embedding"], 1)
+    inp["mask_cond_fea"] = per(inp["mask_cond_fea"], 2)
+    rows = torch.cat([b * f + (torch.arange(f) % fl) for b in (0, 1)])
+    for k in ("full_mask", "face_mask", "lip_mask"):
+        inp[k] = [t[rows] for t in inp[k]]
+    W = m._weights()
+    full = DenoiseEngine(W, size, size, f)
+    full.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
+    full.set_timestep(inp["timestep"])
+    ref = full.forward_only(inp["sample"].float())[:, :, :fl]
+    shard = DenoiseEngine(W, size, size, f, Shard(frames=tuple(range(fl)), emulate_group=R))
+    shard.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
+    shard.set_timestep(inp["timestep"])
+    out = shard.forward_only(inp["sample"][:, :, :fl].float())
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    print(f"emulated rank 0 of {R} vs unsharded frames [0, {fl}): rel L2 = {err:.3e}")
+    assert err < 2e-3
+
+
 def test_strict_state_dict_and_api_surface(model):
     m, sd = model
     assert len(m.state_dict()) == 1946
