@@ -50,6 +50,7 @@ class Shard:
 
 class PackedWeights:
     """Device-resident, kernel-ready copies of the state dict (packed once per model load)."""
+    kind = "3d"        # refnet.ReferenceNetWeights sets "2d": resnets + spatial blocks only, no output head
 
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: UNetConfig, device, dtype):
         self.cfg = cfg
@@ -99,14 +100,15 @@ class PackedWeights:
         put("conv_in.b", sd["conv_in.bias"])
         lin("time_embedding.linear_1")
         lin("time_embedding.linear_2")
-        norm("conv_norm_out")
-        w_out = ops.pack_conv3x3_weight(sd["conv_out.weight"])       # [Cl, 9*C0] -> padded to 8 rows
-        wo = torch.zeros(8, w_out.shape[1], dtype=w_out.dtype, device=w_out.device)
-        wo[:w_out.shape[0]] = w_out
-        bo = torch.zeros(8, dtype=w_out.dtype, device=w_out.device)
-        bo[:w_out.shape[0]] = sd["conv_out.bias"]
-        put("conv_out.w", wo)
-        put("conv_out.b", bo)
+        if self.kind == "3d":
+            norm("conv_norm_out")
+            w_out = ops.pack_conv3x3_weight(sd["conv_out.weight"])       # [Cl, 9*C0] -> padded to 8 rows
+            wo = torch.zeros(8, w_out.shape[1], dtype=w_out.dtype, device=w_out.device)
+            wo[:w_out.shape[0]] = w_out
+            bo = torch.zeros(8, dtype=w_out.dtype, device=w_out.device)
+            bo[:w_out.shape[0]] = sd["conv_out.bias"]
+            put("conv_out.w", wo)
+            put("conv_out.b", bo)
 
         temb_w, temb_b = [], []
         self.temb_off: Dict[str, int] = {}
@@ -143,7 +145,7 @@ class PackedWeights:
                     put(f"{tb}.attn2.kv", torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], 0))
                     lin(f"{tb}.attn2.to_out.0")
                     ff(f"{tb}.ff")
-                if l.audio:
+                if l.audio and self.kind == "3d":
                     n = l.audio
                     tb = f"{n}.transformer_blocks.0"
                     norm(f"{n}.norm"); lin(f"{n}.proj_in"); lin(f"{n}.proj_out")
@@ -164,7 +166,7 @@ class PackedWeights:
                     self.t[f"{tb}.zero.b"] = torch.stack([sd[f"{tb}.zero_conv_{r}.bias"].float()
                                                           for r in ("full", "face", "lip")], 0).to(device)
                     ff(f"{tb}.ff")
-                if l.motion and l.motion_executed:
+                if l.motion and l.motion_executed and self.kind == "3d":
                     tt = f"{l.motion}.temporal_transformer"
                     tb = f"{tt}.transformer_blocks.0"
                     norm(f"{tt}.norm"); lin(f"{tt}.proj_in"); lin(f"{tt}.proj_out")

@@ -4,9 +4,9 @@ read  mode: attaches to hallo_b200's UNet3DConditionModel; update(writer) pairs 
             spatial transformer blocks in the reference's order (stable sort by -norm1 width over module DFS order,
             :404-453) and hands them to the engine, cast to fp16 first exactly like the reference (Q4).  The
             read-side arithmetic (KV concat, CFG handling, motion-frame hand-off; :233-327) lives in the kernels.
-write mode: banks `norm1(hidden_states)` of every BasicTransformerBlock-like module of the given (reference,
-            PyTorch) ReferenceNet through forward pre-hooks; the ReferenceNet itself is outside the hot path
-             and stays whatever module the caller passes in.
+write mode: with hallo_b200's engine-backed ReferenceNet (models/unet_2d_condition.py) the banks are the engine's
+            norm1 buffers, read directly; with any other (reference, PyTorch) ReferenceNet, `norm1(hidden_states)` of
+            every BasicTransformerBlock-like module is banked through forward pre-hooks.
 """
 from __future__ import annotations
 
@@ -43,7 +43,10 @@ class ReferenceAttentionControl:
         self.do_classifier_free_guidance = do_classifier_free_guidance
         self._hooks = []
         self._writer_blocks: List[torch.nn.Module] = []
-        if mode == "write" and reference_attn:
+        self._engine_writer = mode == "write" and hasattr(unet, "banks") and hasattr(unet, "arch")
+        if self._engine_writer:
+            pass      # hallo_b200's own ReferenceNet: forward() leaves the banks in unet.banks, nothing to hook
+        elif mode == "write" and reference_attn:
             blocks = [m for m in _dfs(unet) if _is_writer_block(m)]
             blocks = sorted(blocks, key=lambda x: -x.norm1.normalized_shape[0])
             for m in blocks:
@@ -62,6 +65,8 @@ class ReferenceAttentionControl:
 
     # writer-side view used by update()
     def banks_in_pairing_order(self) -> List[torch.Tensor]:
+        if self._engine_writer:
+            return [self.unet.banks[name] for name, _ in reader_bank_order(self.unet.arch)] if self.unet.banks else []
         return [m.bank[0] for m in self._writer_blocks if len(m.bank) > 0]
 
     def update(self, writer, dtype=torch.float16):
@@ -83,6 +88,8 @@ class ReferenceAttentionControl:
     def clear(self):
         if self.mode == "read":
             self.unet.set_banks({})
+        elif self._engine_writer:
+            self.unet.banks = {}
         else:
             # the pipeline builds a new writer per window (face_animate.py:300-313): drop this writer's pre-hooks with
             # its banks, or every window would leave 16 more hooks (and norm1 + clone calls) on the ReferenceNet

@@ -314,3 +314,31 @@ def sinusoid_pe(max_len: int, d_model: int):
     pe[0, :, 0::2] = torch.sin(position * div_term)
     pe[0, :, 1::2] = torch.cos(position * div_term)
     return pe
+
+
+# ---------------------------------------------------------------------------------------------
+# ReferenceNet (hallo/models/unet_2d_condition.py: the SD-1.5 UNet2D that produces the K/V banks)
+# ---------------------------------------------------------------------------------------------
+def param_spec_2d(cfg: UNetConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """State-dict keys of the reference's UNet2DConditionModel built from the SD-1.5 config: the resnet / spatial
+    transformer / sampler subset of the 3D walk (same names).  The reference deletes conv_norm_out / conv_act / conv_out
+    (the ReferenceNet returns after the up blocks), so they are not part of the contract: 682 entries, verified against
+    the instantiated reference class (tests/golden/unet2d_state_dict_keys.json)."""
+    keys: List[Tuple[str, Tuple[int, ...], str]] = []
+    temb = cfg.time_embed_dim
+    c0 = cfg.block_out_channels[0]
+    _conv(keys, "conv_in", c0, cfg.in_channels, 3)
+    _lin(keys, "time_embedding.linear_1", temb, c0)
+    _lin(keys, "time_embedding.linear_2", temb, temb)
+    for b in build_blocks(cfg):
+        if b.extra_resnet is not None:
+            _resnet(keys, b.extra_resnet, temb)
+        for l in b.layers:
+            _resnet(keys, l.resnet, temb)
+            if l.attn:
+                _spatial_tf(keys, l.attn, b.channels, cfg.cross_attention_dim)
+        if b.downsampler:
+            _conv(keys, f"{b.downsampler}.conv", b.channels, b.channels, 3)
+        if b.upsampler:
+            _conv(keys, f"{b.upsampler}.conv", b.channels, b.channels, 3)
+    return keys

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .spec import UNetConfig, param_spec, reader_bank_order, sinusoid_pe
+from .spec import UNetConfig, param_spec, param_spec_2d, reader_bank_order, sinusoid_pe
 
 
 def _gen(seed: int, key: str) -> torch.Generator:
@@ -28,9 +28,9 @@ def _gen(seed: int, key: str) -> torch.Generator:
 
 
 def synth_state_dict(cfg: UNetConfig, seed: int = 0, dtype=torch.float32,
-                     only_prefix: Optional[str] = None) -> Dict[str, torch.Tensor]:
+                     only_prefix: Optional[str] = None, spec=None) -> Dict[str, torch.Tensor]:
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, kind in param_spec(cfg):
+    for key, shape, kind in (param_spec(cfg) if spec is None else spec):
         if only_prefix is not None and not key.startswith(only_prefix):
             continue
         g = _gen(seed, key)
@@ -79,6 +79,22 @@ def synth_state_dict_device(cfg: UNetConfig, device, seed: int = 0) -> Dict[str,
         else:
             raise ValueError(kind)
     return sd
+
+
+def synth_state_dict_2d(cfg: UNetConfig, seed: int = 1, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the ReferenceNet (SD-1.5 UNet2D, hallo/models/unet_2d_condition.py): same per-key streams
+    and distributions as the denoising UNet, its own seed."""
+    return synth_state_dict(cfg, seed=seed, dtype=dtype, spec=param_spec_2d(cfg))
+
+
+def synth_refnet_inputs(cfg: UNetConfig, h: int, w: int, seed: int = 7, dtype=torch.float32) -> dict:
+    """What FaceAnimatePipeline feeds the ReferenceNet (face_animate.py:386-395): the VAE latents of the reference image
+    and the nm motion frames, repeated for the two CFG halves -> (2*(1+nm), 4, h, w); timestep 0; the (2, 4, 768)
+    image tokens [uncond, cond]."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lat = torch.randn(1 + cfg.n_motion_frames, cfg.in_channels, h, w, generator=g)
+    ehs = torch.randn(2, 4, cfg.cross_attention_dim, generator=g)
+    return dict(sample=lat.repeat(2, 1, 1, 1).to(dtype), timestep=0, encoder_hidden_states=ehs.to(dtype))
 
 
 def mask_levels(h: int, w: int):

@@ -82,3 +82,11 @@ class Attention(nn.Module):
         # 0.27.2 drops kwargs the processor does not name (e.g. video_length) with a warning
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
                               attention_mask=attention_mask)
+
+
+class AttnAddedKVProcessor:      # import-only in unet_2d_condition.py:56-58 (set_default_attn_processor is never called)
+    pass
+
+
+ADDED_KV_ATTENTION_PROCESSORS = (AttnAddedKVProcessor,)
+CROSS_ATTENTION_PROCESSORS = (AttnProcessor, AttnProcessor2_0)

@@ -34,8 +34,10 @@ class Timesteps(nn.Module):
 
 
 class TimestepEmbedding(nn.Module):
-    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None, post_act_fn=None, cond_proj_dim=None,
+                 sample_proj_bias=True):
         super().__init__()
+        assert post_act_fn is None and cond_proj_dim is None and act_fn in ("silu", "swish") and sample_proj_bias
         self.linear_1 = nn.Linear(in_channels, time_embed_dim)
         self.act = nn.SiLU()
         self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim)
@@ -47,3 +49,19 @@ class TimestepEmbedding(nn.Module):
 class SinusoidalPositionalEmbedding(nn.Module):
     def __init__(self, *a, **k):
         raise NotImplementedError("import-only in the reference hot path")
+
+
+def _import_only(name):
+    def __init__(self, *a, **k):
+        raise NotImplementedError(f"{name}: import-only in the reference's SD-1.5 ReferenceNet (unet_2d_condition.py:59-66)")
+    return type(name, (nn.Module,), {"__init__": __init__})
+
+
+GaussianFourierProjection = _import_only("GaussianFourierProjection")
+GLIGENTextBoundingboxProjection = _import_only("GLIGENTextBoundingboxProjection")
+ImageHintTimeEmbedding = _import_only("ImageHintTimeEmbedding")
+ImageProjection = _import_only("ImageProjection")
+ImageTimeEmbedding = _import_only("ImageTimeEmbedding")
+TextImageProjection = _import_only("TextImageProjection")
+TextImageTimeEmbedding = _import_only("TextImageTimeEmbedding")
+TextTimeEmbedding = _import_only("TextTimeEmbedding")

@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from hallo_b200.spec import UNetConfig  # noqa: E402
-from hallo_b200.synth import host_threads, synth_inputs, synth_state_dict  # noqa: E402
+from hallo_b200.synth import (host_threads, synth_inputs, synth_refnet_inputs, synth_state_dict,  # noqa: E402
+                              synth_state_dict_2d)
 from oracle import ref_host  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -38,8 +39,43 @@ def checksum(t: torch.Tensor) -> float:
     return float(t.double().abs().sum())
 
 
+def make_refnet():
+    """ReferenceNet fixtures: the unmodified reference UNet2D (hallo/models/unet_2d_condition.py) with the reference's
+    own write-mode ReferenceAttentionControl, on hallo_b200.synth weights / inputs at latent 8x8:
+      unet2d_state_dict_keys.json   key -> shape (682 entries)
+      refnet_h8.pt                  last-up-block features (fp16), the control's bank pairing order, per-bank
+                                    statistics and three full banks (one per width + the mid block)"""
+    cfg = UNetConfig()
+    unet = ref_host.build_reference_unet2d()
+    with open(os.path.join(GOLD, "unet2d_state_dict_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in unet.state_dict().items()}, f, indent=0, sort_keys=True)
+    sd = synth_state_dict_2d(cfg)
+    unet.load_state_dict(sd, strict=True)
+    c = dict(h=8, seed=7)
+    inp = synth_refnet_inputs(cfg, c["h"], c["h"], seed=c["seed"])
+    out, banks, names = ref_host.run_reference_net(unet, inp)
+    keep = ("down_blocks.0.attentions.0", "up_blocks.2.attentions.1", "mid_block.attentions.0")
+    fx = dict(case=c, out=out.half(), bank_order=names,
+              bank_stats={n: dict(shape=list(b.shape), mean=float(b.mean()), std=float(b.std()), abs_sum=checksum(b))
+                          for n, b in zip(names, banks)},
+              banks={n: b.half() for n, b in zip(names, banks) if n in keep},
+              input_checksums=dict(sample=checksum(inp["sample"]), ehs=checksum(inp["encoder_hidden_states"])),
+              weight_checksums={k: checksum(sd[k]) for k in ("conv_in.weight", "mid_block.attentions.0.proj_in.weight")},
+              torch_version=torch.__version__)
+    path = os.path.join(GOLD, "refnet_h8.pt")
+    torch.save(fx, path)
+    print("wrote", path, tuple(out.shape), "std", float(out.std()))
+
+
 def main():
     only = sys.argv[sys.argv.index("--only") + 1:] if "--only" in sys.argv else None
+    if only is not None and "refnet" in only:
+        torch.set_num_threads(host_threads())
+        os.makedirs(GOLD, exist_ok=True)
+        make_refnet()
+        only = [o for o in only if o != "refnet"]
+        if not only:
+            return
     torch.set_num_threads(host_threads())
     os.makedirs(GOLD, exist_ok=True)
     cfg = UNetConfig()
@@ -79,6 +115,8 @@ def main():
         path = os.path.join(GOLD, f"unet_fwd_h{c['h']}_f{c['f']}.pt")
         torch.save(fx, path)
         print("wrote", path, tuple(out.shape), "std", float(out.std()))
+    if only is None:
+        make_refnet()
 
 
 if __name__ == "__main__":

@@ -310,3 +310,73 @@ def denoise_loop(sd: SD, cfg: UNetConfig, inp: dict, latents: torch.Tensor, n_st
         v = vu + guidance * (vc - vu)
         latents = sch.step(v, t, latents, n_steps).to(latents.dtype)
     return latents
+
+
+# ----------------------------------------------------------------------------- ReferenceNet (SD-1.5 UNet2D, write mode)
+def _resnet2d(sd: SD, rs: ResnetSpec, x, temb, cfg: UNetConfig):
+    """diffusers ResnetBlock2D as used by hallo/models/unet_2d_blocks.py (time_embedding_norm="default")."""
+    n = rs.name
+    h = F.silu(F.group_norm(x, cfg.norm_num_groups, sd[f"{n}.norm1.weight"], sd[f"{n}.norm1.bias"], cfg.norm_eps))
+    h = conv2d(sd, f"{n}.conv1", h)
+    h = h + linear(sd, f"{n}.time_emb_proj", F.silu(temb))[:, :, None, None]
+    h = F.silu(F.group_norm(h, cfg.norm_num_groups, sd[f"{n}.norm2.weight"], sd[f"{n}.norm2.bias"], cfg.norm_eps))
+    h = conv2d(sd, f"{n}.conv2", h)
+    if rs.has_shortcut:
+        x = conv2d(sd, f"{n}.conv_shortcut", x, padding=0)
+    return x + h
+
+
+def _transformer2d_write(sd: SD, name: str, x, ehs, banks: dict, cfg: UNetConfig):
+    """Transformer2DModel.forward (transformer_2d.py:245-420: GN eps 1e-6, 1x1 proj_in, NLC) around the hacked
+    BasicTransformerBlock forward in WRITE mode (mutual_self_attention.py:223-232, 329-366): bank norm1(x), plain
+    self-attention, image cross-attention with the tokens TILED over the batch (`.repeat(tmp, 1, 1)`, :340-346), FF."""
+    n, c, h, w = x.shape
+    H = cfg.heads
+    t = F.group_norm(x, cfg.norm_num_groups, sd[f"{name}.norm.weight"], sd[f"{name}.norm.bias"], 1e-6)
+    t = conv2d(sd, f"{name}.proj_in", t, padding=0).permute(0, 2, 3, 1).reshape(n, h * w, c)
+    tb = f"{name}.transformer_blocks.0"
+    n1 = layer_norm(sd, f"{tb}.norm1", t)
+    banks[name] = n1.clone()
+    t = attention(sd, f"{tb}.attn1", n1, n1, H) + t
+    ctx = ehs.repeat(n // ehs.shape[0], 1, 1)
+    t = attention(sd, f"{tb}.attn2", layer_norm(sd, f"{tb}.norm2", t), ctx, H) + t
+    t = feed_forward(sd, f"{tb}.ff", layer_norm(sd, f"{tb}.norm3", t)) + t
+    y = t.reshape(n, h, w, c).permute(0, 3, 1, 2)
+    return conv2d(sd, f"{name}.proj_out", y, padding=0) + x
+
+
+@torch.no_grad()
+def reference_net_forward(sd: SD, cfg: UNetConfig, inp: dict):
+    """UNet2DConditionModel.forward of the ReferenceNet (hallo/models/unet_2d_condition.py:905-1356, post_process=False)
+    with ReferenceAttentionControl(mode="write") attached.  inp: sample (n, 4, h, w), timestep, encoder_hidden_states
+    (2, tokens, 768).  Returns (features of the last up block, {attention block name: bank (n, L, C)})."""
+    x = inp["sample"]
+    t = torch.as_tensor(inp["timestep"]).reshape(-1).expand(x.shape[0])
+    temb = timestep_embedding(sd, t, cfg.block_out_channels[0], x.dtype)
+    ehs = inp["encoder_hidden_states"]
+    banks: dict = {}
+    x = conv2d(sd, "conv_in", x)
+    skips = [x]
+    for b in build_blocks(cfg):
+        if b.kind in ("down_x", "down"):
+            for l in b.layers:
+                x = _resnet2d(sd, l.resnet, x, temb, cfg)
+                if l.attn:
+                    x = _transformer2d_write(sd, l.attn, x, ehs, banks, cfg)
+                skips.append(x)
+            if b.downsampler:
+                x = conv2d(sd, f"{b.downsampler}.conv", x, stride=2, padding=1)
+                skips.append(x)
+        elif b.kind == "mid":
+            x = _resnet2d(sd, b.extra_resnet, x, temb, cfg)
+            x = _transformer2d_write(sd, b.layers[0].attn, x, ehs, banks, cfg)
+            x = _resnet2d(sd, b.layers[0].resnet, x, temb, cfg)
+        else:
+            for l in b.layers:
+                x = torch.cat([x, skips.pop()], dim=1)
+                x = _resnet2d(sd, l.resnet, x, temb, cfg)
+                if l.attn:
+                    x = _transformer2d_write(sd, l.attn, x, ehs, banks, cfg)
+            if b.upsampler:
+                x = conv2d(sd, f"{b.upsampler}.conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    return x, banks

@@ -71,3 +71,38 @@ def run_reference_unet(unet, inp: dict):
                 audio_embedding=inp["audio_embedding"], mask_cond_fea=inp["mask_cond_fea"],
                 full_mask=inp["full_mask"], face_mask=inp["face_mask"], lip_mask=inp["lip_mask"],
                 motion_scale=inp["motion_scale"], return_dict=False)[0]
+
+
+# ----------------------------------------------------------------------------- ReferenceNet (unmodified reference UNet2D)
+def build_reference_unet2d(base_cfg=None):
+    """hallo.models.unet_2d_condition.UNet2DConditionModel from the SD-1.5 config (scripts/inference.py:196-199 uses
+    from_pretrained, which returns an eval() module; there is no dropout, so mode does not change the arithmetic)."""
+    assert available(), "reference tree not present"
+    _activate()
+    from hallo.models.unet_2d_condition import UNet2DConditionModel  # unmodified reference file
+    from hallo_b200.spec import SD15_UNET_CONFIG
+    unet = UNet2DConditionModel.from_config(dict(SD15_UNET_CONFIG if base_cfg is None else base_cfg))
+    unet.requires_grad_(False)
+    unet.eval()
+    return unet
+
+
+@torch.no_grad()
+def run_reference_net(unet2d, inp: dict):
+    """ReferenceNet forward with the reference's own ReferenceAttentionControl(mode="write") attached
+    (face_animate.py:300-306, 386-393).  Returns (sample, [bank per writer block in the control's pairing order],
+    [module name per bank])."""
+    _activate()
+    from hallo.models.mutual_self_attention import ReferenceAttentionControl
+    writer = ReferenceAttentionControl(unet2d, do_classifier_free_guidance=True, mode="write", batch_size=1,
+                                       fusion_blocks="full")
+    out = unet2d(inp["sample"], torch.tensor(inp["timestep"]), encoder_hidden_states=inp["encoder_hidden_states"],
+                 return_dict=False)[0]
+    from hallo.models.attention import BasicTransformerBlock
+    mods = [(n, m) for n, m in unet2d.named_modules() if isinstance(m, BasicTransformerBlock)]
+    # the control's own order: torch_dfs order (down, up, mid) stably sorted by -norm1 width (mutual_self_attention.py:371-385)
+    mods = sorted(mods, key=lambda nm: -nm[1].norm1.normalized_shape[0])
+    banks = [m.bank[0].clone() for _, m in mods]
+    names = [n.rsplit(".transformer_blocks", 1)[0] for n, _ in mods]
+    writer.clear()
+    return out, banks, names

@@ -116,3 +116,63 @@ def test_ddim_schedule_known_answers():
     # last step lands on x0 exactly (final_alpha_cumprod = 1)
     a = s.alphas_cumprod[24]
     assert torch.allclose(s.step(v, 24, x, 40), a.sqrt() * x - (1 - a).sqrt() * v, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ ReferenceNet (8f row 1)
+def test_refnet_state_dict_contract_matches_reference_keys(cfg):
+    """The 682-entry key/shape list of the reference's UNet2DConditionModel (dumped from the reference class itself)."""
+    from hallo_b200.spec import param_spec_2d
+    ref = json.load(open(os.path.join(GOLD, "unet2d_state_dict_keys.json")))
+    mine = {k: list(s) for k, s, _ in param_spec_2d(cfg)}
+    assert len(ref) == 682 and mine == ref
+    from hallo_b200.models.unet_2d_condition import UNet2DConditionModel
+    from hallo_b200.spec import SD15_UNET_CONFIG
+    m = UNet2DConditionModel.from_config(SD15_UNET_CONFIG)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == ref
+
+
+def test_refnet_port_matches_golden(cfg):
+    """oracle/port.reference_net_forward against the fixture produced by the UNMODIFIED reference UNet2D with the
+    reference's own write-mode ReferenceAttentionControl: output features, bank pairing order, every bank's statistics,
+    three banks element-wise."""
+    from hallo_b200.synth import synth_refnet_inputs, synth_state_dict_2d
+    from oracle import port
+    fx = torch.load(os.path.join(GOLD, "refnet_h8.pt"), weights_only=False)
+    torch.set_num_threads(host_threads())
+    sd2 = synth_state_dict_2d(cfg)
+    inp = synth_refnet_inputs(cfg, fx["case"]["h"], fx["case"]["h"], seed=fx["case"]["seed"])
+    assert abs(float(inp["sample"].double().abs().sum()) - fx["input_checksums"]["sample"]) < 1e-6 * fx["input_checksums"]["sample"]
+    out, banks = port.reference_net_forward(sd2, cfg, inp)
+    assert rel_l2(out, fx["out"].float()) < 1e-3                        # fixture stored in fp16
+    assert fx["bank_order"] == [n for n, _ in reader_bank_order(cfg)]   # A11: the reference control's own pairing order
+    for n, st in fx["bank_stats"].items():
+        b = banks[n]
+        assert list(b.shape) == st["shape"]
+        assert abs(float(b.double().abs().sum()) - st["abs_sum"]) < 1e-4 * st["abs_sum"], n
+    for n, b in fx["banks"].items():
+        assert rel_l2(banks[n], b.float()) < 1e-3, n
+
+
+def test_refnet_port_matches_reference_host(cfg):
+    """Live cross-check where /root/reference exists: hosted reference UNet2D + reference writer vs the port (fp32)."""
+    from oracle import port, ref_host
+    if not ref_host.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from hallo_b200.synth import synth_refnet_inputs, synth_state_dict_2d
+    torch.set_num_threads(host_threads())
+    sd2 = synth_state_dict_2d(cfg)
+    unet = ref_host.build_reference_unet2d()
+    unet.load_state_dict(sd2, strict=True)
+    inp = synth_refnet_inputs(cfg, 16, 16, seed=11)
+    out, banks, names = ref_host.run_reference_net(unet, inp)
+    o2, b2 = port.reference_net_forward(sd2, cfg, inp)
+    assert names == [n for n, _ in reader_bank_order(cfg)]
+    assert rel_l2(o2, out) < 2e-5
+    assert max(rel_l2(b2[n], b) for n, b in zip(names, banks)) < 2e-5
+    # Q10: the image tokens are tiled over the 6 samples (n % 2), not interleaved (n // 3): a restatement with
+    # repeat_interleave must NOT match
+    inp_sw = dict(inp)
+    wrong = inp["encoder_hidden_states"].repeat_interleave(3, dim=0)
+    inp_sw["encoder_hidden_states"] = wrong
+    o3, _ = port.reference_net_forward(sd2, cfg, inp_sw)
+    assert rel_l2(o3, out) > 1e-3
