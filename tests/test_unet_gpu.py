@@ -99,10 +99,12 @@ def test_unet_forward_run_to_run_reproducibility(model):
 
 def test_pixel_transposed_motion_modules_on_one_gpu(model):
     """The frame-sharded path (engine._motion_px: frame <-> pixel swap around every motion module) without a second GPU:
-    with a window whose frames repeat with period fl, the rows the other ranks would send are copies of the local ones,
-    which is exactly what Shard(emulate_group=R) substitutes -- so rank 0's emulated shard must reproduce frames
-    [0, fl) of the unsharded forward.  Checks the x18 layout, the positional-encoding indices, the local-frame window
-    slicing and the CFG-local step tail; the peer-memory transport itself is tests/test_multigpu_gpu.py."""
+    with a window whose frames repeat with period fl AND the temporal positional encoding zeroed (so that temporal
+    attention cannot tell the repeats apart and they stay identical through every layer), the rows the other ranks
+    would send are copies of the local ones -- exactly what Shard(emulate_group=R) substitutes -- so rank 0's emulated
+    shard must reproduce frames [0, fl) of the unsharded forward.  Checks the x18 layout, the pixel-slice bookkeeping,
+    the local-frame window slicing and the row order of the swaps; the positional indices and the peer-memory
+    transport itself are covered by tests/test_multigpu_gpu.py."""
     from hallo_b200.dist import window_inputs_to_device
     from hallo_b200.engine import DenoiseEngine, Shard
     from hallo_b200.spec import UNetConfig
@@ -120,15 +122,25 @@ def test_pixel_transposed_motion_modules_on_one_gpu(model):
     for k in ("full_mask", "face_mask", "lip_mask"):
         inp[k] = [t[rows] for t in inp[k]]
     W = m._weights()
-    full = DenoiseEngine(W, size, size, f)
-    full.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
-    full.set_timestep(inp["timestep"])
-    ref = full.forward_only(inp["sample"].float())[:, :, :fl]
-    shard = DenoiseEngine(W, size, size, f, Shard(frames=tuple(range(fl)), emulate_group=R))
-    shard.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
-    shard.set_timestep(inp["timestep"])
-    out = shard.forward_only(inp["sample"][:, :, :fl].float())
-    torch.cuda.synchronize()
+    pe_keys = [k for k in W.t if k.endswith(".pe")]
+    saved = {k: W.t[k].clone() for k in pe_keys}
+    try:
+        for k in pe_keys:
+            W.t[k].zero_()
+        full = DenoiseEngine(W, size, size, f)
+        full.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
+        full.set_timestep(inp["timestep"])
+        ref_all = full.forward_only(inp["sample"].float())
+        assert rel_l2(ref_all[:, :, fl:2 * fl], ref_all[:, :, :fl]) < 1e-6        # the premise: repeats stay identical
+        ref = ref_all[:, :, :fl]
+        shard = DenoiseEngine(W, size, size, f, Shard(frames=tuple(range(fl)), emulate_group=R))
+        shard.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
+        shard.set_timestep(inp["timestep"])
+        out = shard.forward_only(inp["sample"][:, :, :fl].float())
+        torch.cuda.synchronize()
+    finally:
+        for k in pe_keys:
+            W.t[k].copy_(saved[k])
     err = rel_l2(out, ref)
     print(f"emulated rank 0 of {R} vs unsharded frames [0, {fl}): rel L2 = {err:.3e}")
     assert err < 2e-3

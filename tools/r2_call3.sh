@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 call 3 (2 GPUs): single-GPU checks of the scatter kernels + emulated shard first; then the real 2-rank runs.
 mkdir -p gpurun_out
-CUDA_VISIBLE_DEVICES=0 timeout 900 python -m pytest tests/test_aux_gpu.py tests/test_unet_gpu.py tests/test_attention_gpu.py -q -m gpu -x -p no:cacheprovider -rA 2>&1 | grep -v "^PASSED" > gpurun_out/r2c_tests_1gpu.log
+CUDA_VISIBLE_DEVICES=0 timeout 900 python -m pytest tests/test_aux_gpu.py tests/test_unet_gpu.py tests/test_refnet_gpu.py -q -m gpu -x -p no:cacheprovider -rA 2>&1 | grep -v "^PASSED" > gpurun_out/r2c_tests_1gpu.log
 rc=${PIPESTATUS[0]}
 echo "1-GPU tests exit $rc" | tee gpurun_out/r2c_summary.txt
 tail -5 gpurun_out/r2c_tests_1gpu.log >> gpurun_out/r2c_summary.txt
