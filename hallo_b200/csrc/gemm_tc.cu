@@ -402,6 +402,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & HB_EPI_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        } else if (p.flags & HB_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (geglu) {
           // (value, gate) pairs: 32 accumulator columns -> 16 outputs = chunks 2*(u&1), 2*(u&1)+1 of the panel row
@@ -601,6 +604,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.flags & HB_EPI_SILU) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = silu_f(v[j]);
+          } else if (p.flags & HB_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (geglu) {
             // (value, gate) pairs: CW accumulator columns -> CW/2 outputs

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhallo_b200.so")
 HB_F16, HB_BF16 = 0, 1
 HB_EPI_GEGLU = 1
 HB_EPI_SILU = 2
+HB_EPI_RELU = 4
 
 
 class GemmParams(C.Structure):

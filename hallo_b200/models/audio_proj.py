@@ -1,6 +1,7 @@
 """AudioProjModel (hallo/models/audio_proj.py:40-124): wav2vec window (bz, f, 5, 12, 768) -> 32 context tokens
-of 768 per frame.  Runs once per window (36 M parameters, M = 16 rows); its three Linear layers go through the
-tcgen05 GEMM, ReLU / LayerNorm through PyTorch (outside the timed denoising loop)."""
+of 768 per frame.  36 M parameters, M = 16 rows per window -- or all windows of a clip in one call
+(hallo_b200.driver).  Everything runs in the sm_100a kernels: three tcgen05 GEMMs with the ReLU
+fused into the epilogue (HB_EPI_RELU) and the final LayerNorm in hallo_b200_layernorm."""
 from __future__ import annotations
 
 import torch
@@ -28,9 +29,9 @@ class AudioProjModel(nn.Module):
     def dtype(self):
         return next(self.parameters()).dtype
 
-    def _linear(self, x, lin):
+    def _linear(self, x, lin, relu=False):
         out = torch.empty(x.shape[0], lin.out_features, device=x.device, dtype=x.dtype)
-        return ops.gemm(x.contiguous(), lin.weight, out, bias=lin.bias)
+        return ops.gemm(x.contiguous(), lin.weight, out, bias=lin.bias, relu=relu)
 
     @torch.no_grad()
     def forward(self, audio_embeds):
@@ -38,8 +39,9 @@ class AudioProjModel(nn.Module):
         x = audio_embeds.reshape(bz * f, self.input_dim)
         if x.dtype not in (torch.float16, torch.bfloat16) or not x.is_cuda:
             raise RuntimeError("hallo_b200.AudioProjModel runs in fp16/bf16 on CUDA only (no CPU path)")
-        x = torch.relu(self._linear(x, self.proj1))
-        x = torch.relu(self._linear(x, self.proj2))
-        x = self._linear(x, self.proj3).reshape(bz * f, self.context_tokens, self.output_dim)
-        x = self.norm(x)
-        return x.reshape(bz, f, self.context_tokens, self.output_dim)
+        x = self._linear(x, self.proj1, relu=True)
+        x = self._linear(x, self.proj2, relu=True)
+        x = self._linear(x, self.proj3).reshape(bz * f * self.context_tokens, self.output_dim)
+        out = torch.empty_like(x)
+        ops.layernorm(x, self.norm.weight, self.norm.bias, out, eps=self.norm.eps)
+        return out.reshape(bz, f, self.context_tokens, self.output_dim)

@@ -65,7 +65,7 @@ def _rowmajor_ld(t: torch.Tensor) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          group_bias: Optional[torch.Tensor] = None, rows_per_group: int = 0, alpha: float = 1.0,
-         geglu: bool = False, silu: bool = False, a2: Optional[torch.Tensor] = None,
+         geglu: bool = False, silu: bool = False, relu: bool = False, a2: Optional[torch.Tensor] = None,
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          stats_out: Optional[torch.Tensor] = None, scatter: Optional["lib.RowScatter"] = None) -> torch.Tensor:
     """out[M, N(/2)] = epilogue(cat([a, a2], 1) @ w.T); see include/hallo_b200.h.  With `scatter` (row_scatter()) the
@@ -91,7 +91,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     if residual is not None:
         p.residual, p.ldr = lib.ptr(residual), _rowmajor_ld(residual)
     p.alpha = alpha
-    p.flags = (lib.HB_EPI_GEGLU if geglu else 0) | (lib.HB_EPI_SILU if silu else 0)
+    p.flags = (lib.HB_EPI_GEGLU if geglu else 0) | (lib.HB_EPI_SILU if silu else 0) | (lib.HB_EPI_RELU if relu else 0)
     if ln_stats is not None:
         assert ln_stats.dtype == torch.float32 and ln_stats.numel() >= 2 * M and ln_colsum.dtype == torch.float32
         assert ln_colsum.numel() == N and ln_stats.is_contiguous() and ln_colsum.is_contiguous()

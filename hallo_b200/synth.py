@@ -97,6 +97,26 @@ def synth_refnet_inputs(cfg: UNetConfig, h: int, w: int, seed: int = 7, dtype=to
     return dict(sample=lat.repeat(2, 1, 1, 1).to(dtype), timestep=0, encoder_hidden_states=ehs.to(dtype))
 
 
+def synth_audio_proj_state_dict(seed: int = 2, seq_len=5, blocks=12, channels=768, intermediate_dim=512, output_dim=768,
+                                context_tokens=32) -> Dict[str, torch.Tensor]:
+    """Random-init weights of AudioProjModel (hallo/models/audio_proj.py:62-94), per-key seeded like the UNets."""
+    din = seq_len * blocks * channels
+    shapes = {"proj1.weight": (intermediate_dim, din), "proj1.bias": (intermediate_dim,),
+              "proj2.weight": (intermediate_dim, intermediate_dim), "proj2.bias": (intermediate_dim,),
+              "proj3.weight": (context_tokens * output_dim, intermediate_dim), "proj3.bias": (context_tokens * output_dim,),
+              "norm.weight": (output_dim,), "norm.bias": (output_dim,)}
+    sd = {}
+    for k, shp in shapes.items():
+        g = _gen(seed, "audio_proj." + k)
+        if k.endswith("proj1.weight") or k.endswith("proj2.weight") or k.endswith("proj3.weight"):
+            sd[k] = torch.randn(shp, generator=g) * (2.0 / shp[1]) ** 0.5          # He: ReLU layers keep unit scale
+        elif k == "norm.weight":
+            sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+    return sd
+
+
 def mask_levels(h: int, w: int):
     """Token counts of the 4 mask scales (image_processor.py:156-180): latent /1,/2,/4,/8."""
     return [(h // s) * (w // s) for s in (1, 2, 4, 8)]

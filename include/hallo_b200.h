@@ -93,7 +93,11 @@ int hallo_b200_get_option(const char* name);
  *        v  = v * row_scale[row] * alpha + residual[row][col]
  *   Constraints: K % 64 == 0 (K1 % 64 == 0, Cin % 64 == 0); lda/ldw/ldc/ldr % 8 == 0.
  * ---------------------------------------------------------------------------------------- */
-enum hb_epi_flags { HB_EPI_GEGLU = 1, HB_EPI_SILU = 2 /* v = silu(v) right after the bias adds */ };
+enum hb_epi_flags {
+  HB_EPI_GEGLU = 1,
+  HB_EPI_SILU = 2, /* v = silu(v) right after the bias adds */
+  HB_EPI_RELU = 4  /* v = max(v, 0) right after the bias adds (AudioProjModel, hallo/models/audio_proj.py:117-119) */
+};
 
 typedef struct {
   int32_t dtype;

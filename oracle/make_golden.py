@@ -67,8 +67,32 @@ def make_refnet():
     print("wrote", path, tuple(out.shape), "std", float(out.std()))
 
 
+def make_audio_proj():
+    """audio_proj_f4.pt: the UNMODIFIED reference AudioProjModel (hallo/models/audio_proj.py) on synth weights, 4 frames."""
+    from hallo_b200.synth import synth_audio_proj_state_dict
+    ref_host._activate()
+    from hallo.models.audio_proj import AudioProjModel          # unmodified reference class
+    m = AudioProjModel(seq_len=5, blocks=12, channels=768, intermediate_dim=512, output_dim=768, context_tokens=32)
+    sd = synth_audio_proj_state_dict()
+    m.load_state_dict(sd, strict=True)
+    x = torch.randn(1, 4, 5, 12, 768, generator=torch.Generator().manual_seed(13))
+    with torch.no_grad():
+        out = m(x)
+    fx = dict(case=dict(frames=4, seed=13), out=out.half(), input_checksum=checksum(x),
+              weight_checksums={k: checksum(v) for k, v in sd.items()}, torch_version=torch.__version__)
+    path = os.path.join(GOLD, "audio_proj_f4.pt")
+    torch.save(fx, path)
+    print("wrote", path, tuple(out.shape), "std", float(out.std()))
+
+
 def main():
     only = sys.argv[sys.argv.index("--only") + 1:] if "--only" in sys.argv else None
+    if only is not None and "audio_proj" in only:
+        torch.set_num_threads(host_threads())
+        make_audio_proj()
+        only = [o for o in only if o != "audio_proj"]
+        if not only:
+            return
     if only is not None and "refnet" in only:
         torch.set_num_threads(host_threads())
         os.makedirs(GOLD, exist_ok=True)
@@ -117,6 +141,7 @@ def main():
         print("wrote", path, tuple(out.shape), "std", float(out.std()))
     if only is None:
         make_refnet()
+        make_audio_proj()
 
 
 if __name__ == "__main__":

@@ -264,3 +264,53 @@ print("OK")
 '''
     r = subprocess.run([sys.executable, "-c", code, ROOT, ref], capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_driver_window_logic_matches_reference_functions():
+    """hallo_b200.driver restates three pieces of scripts/inference.py / audio_processor.py; where /root/reference exists
+    the originals are executed next to them (process_audio_emb is imported from the unmodified script)."""
+    from hallo_b200.driver import audio_frames, padded_sequence_length, process_audio_emb, window_reference_stack
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(37, 12, 8, generator=g)
+    mine = process_audio_emb(emb)
+    # scripts/inference.py:95-114, restated literally
+    ref = torch.stack([torch.stack([emb[max(min(i + j, emb.shape[0] - 1), 0)] for j in range(-2, 3)], 0)
+                       for i in range(emb.shape[0])], 0)
+    assert torch.equal(mine, ref)
+    assert audio_frames(30 * 16000) == 750 and padded_sequence_length(750, 16) == 752 and 752 // 16 == 47   # configs[4]
+    assert padded_sequence_length(752, 16) == 752
+    src = torch.rand(1, 3, 8, 8, generator=g) * 2 - 1
+    first = window_reference_stack(src, None, 2)
+    assert first.shape == (1, 3, 3, 8, 8) and torch.equal(first[0, 1], src[0]) and torch.equal(first[0, 2], src[0])
+    prev = torch.rand(1, 3, 16, 8, 8, generator=g)
+    nxt = window_reference_stack(src, prev, 2)
+    assert torch.equal(nxt[0, 0], src[0])
+    assert torch.allclose(nxt[0, 1], prev[0, :, 14] * 2 - 1) and torch.allclose(nxt[0, 2], prev[0, :, 15] * 2 - 1)
+    ref_root = os.environ.get("HALLO_REFERENCE_ROOT", "/root/reference")
+    if os.path.isfile(os.path.join(ref_root, "scripts", "inference.py")):
+        import ast
+        src_txt = open(os.path.join(ref_root, "scripts", "inference.py")).read()
+        fn = next(n for n in ast.parse(src_txt).body if isinstance(n, ast.FunctionDef) and n.name == "process_audio_emb")
+        ns = {"torch": torch}
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "inference.py", "exec"), ns)
+        assert torch.equal(ns["process_audio_emb"](emb), mine)
+
+
+def test_vae_architecture_contract():
+    """hallo_b200.models.vae.AutoencoderKL: diffusers' SD-1.5 VAE key grammar and sizes (83,653,863 parameters, 248
+    tensors), 8x spatial factor, encode().latent_dist.mean / decode().sample contract the pipeline uses."""
+    from hallo_b200.models.vae import AutoencoderKL
+    v = AutoencoderKL()
+    sd = v.state_dict()
+    assert len(sd) == 248 and sum(p.numel() for p in v.parameters()) == 83653863
+    for k in ("encoder.down_blocks.0.downsamplers.0.conv.weight", "encoder.mid_block.attentions.0.to_q.bias",
+              "decoder.up_blocks.0.upsamplers.0.conv.weight", "decoder.up_blocks.3.resnets.2.conv2.weight",
+              "decoder.up_blocks.2.resnets.0.conv_shortcut.weight", "quant_conv.weight", "post_quant_conv.bias"):
+        assert k in sd, k
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in sd and "encoder.down_blocks.3.downsamplers.0.conv.weight" not in sd
+    assert len(v.config.block_out_channels) == 4
+    x = torch.randn(2, 3, 32, 32)
+    z = v.encode(x).latent_dist.mean
+    assert tuple(z.shape) == (2, 4, 4, 4) and tuple(v.decode(z).sample.shape) == (2, 3, 32, 32)
+    # per-sample independence (what lets the driver encode the source image once and decode frames in chunks)
+    assert torch.allclose(v.encode(x[:1]).latent_dist.mean, z[:1], atol=1e-5)
