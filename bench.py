@@ -148,6 +148,88 @@ def run_reference_arm(size: int, frames: int, K: int, Wm: int):
                        f"{cores} threads: {t_step:.2f} s per step measured over {K} steps")
 
 
+# ------------------------------------------------------------------------------------------------ configs[4]: clip e2e
+def run_clip(args, rank, world, dev, dt, config):
+    """End-to-end frames/s of a clip: N sequential 16-frame windows with 2 motion frames handed from window to window,
+    every component on the path (random-init SD-1.5 VAE, engine-backed ReferenceNet, conditioning encoders, the 40-step
+    denoising loop, decode), host tensors in, host video out.  One untimed warm-up window (graph capture, cuDNN plans)."""
+    import torch.distributed as dist
+    from hallo_b200.animate.face_animate import FaceAnimatePipeline
+    from hallo_b200.driver import ClipAnimator, process_audio_emb
+    from hallo_b200.models.audio_proj import AudioProjModel
+    from hallo_b200.models.face_locator import FaceLocator
+    from hallo_b200.models.image_proj import ImageProjModel
+    from hallo_b200.models.unet_2d_condition import UNet2DConditionModel
+    from hallo_b200.models.unet_3d import UNet3DConditionModel
+    from hallo_b200.models.vae import AutoencoderKL
+    from hallo_b200.scheduler import DDIMScheduler
+    from hallo_b200.spec import HALLO_UNET_KWARGS, SD15_UNET_CONFIG, UNetConfig
+    from hallo_b200.synth import mask_levels, synth_audio_proj_state_dict, synth_state_dict, synth_state_dict_2d
+    cfg = UNetConfig()
+    H = W = args.size * 8
+    cl = args.frames
+    torch.manual_seed(0)
+    unet = UNet3DConditionModel.from_config(SD15_UNET_CONFIG, **HALLO_UNET_KWARGS)
+    unet.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    refnet = UNet2DConditionModel.from_config(SD15_UNET_CONFIG)
+    refnet.load_state_dict(synth_state_dict_2d(cfg), strict=True)
+    vae = AutoencoderKL().to(memory_format=torch.channels_last)
+    fl_ = FaceLocator(conditioning_embedding_channels=320)
+    torch.nn.init.normal_(fl_.conv_out.weight, std=0.02)                      # de-zeroed so the branch is live
+    ip = ImageProjModel(cross_attention_dim=768, clip_embeddings_dim=512, clip_extra_context_tokens=4)
+    ap_ = AudioProjModel()
+    ap_.load_state_dict(synth_audio_proj_state_dict(), strict=True)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                          prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    pipe = FaceAnimatePipeline(vae=vae, reference_unet=refnet, denoising_unet=unet, face_locator=fl_, scheduler=sched,
+                               image_proj=ip)
+    pipe.to(device=dev, dtype=dt)
+    ap_ = ap_.to(dev, dt)
+    g = torch.Generator().manual_seed(42)
+    n_win = args.windows
+    audio = process_audio_emb(torch.randn((n_win + 1) * cl, 12, 768, generator=g))
+    masks = [torch.rand(1, L, generator=g) for L in mask_levels(args.size, args.size)]
+    kw = dict(source_image_pixels=torch.rand(3, H, W, generator=g) * 2 - 1, source_image_face_region=torch.rand(3, H, W, generator=g),
+              source_image_face_emb=torch.randn(512, generator=g), source_image_full_mask=masks, source_image_face_mask=masks,
+              source_image_lip_mask=masks, width=W, height=H, num_inference_steps=N_DDIM, guidance_scale=3.5)
+    anim = ClipAnimator(pipe, ap_, clip_length=cl, n_motion_frames=cfg.n_motion_frames)
+    anim(audio_emb=audio[:cl], **kw)                                          # warm-up window
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    video = anim(audio_emb=audio[cl:], **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([dt_s], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt_s = float(tmax)
+    phases = {}
+    for wt in anim.window_timings:
+        for k, v in wt.items():
+            phases[k] = phases.get(k, 0.0) + v / len(anim.window_timings)
+    eng = unet.engine(args.size, args.size, cl, pipe._window_shard(cl))
+    if rank == 0:
+        line = {"metric": "end-to-end frames/sec, sliding 16-frame windows with 2 motion-frame overlap (BASELINE.json configs[4])",
+                "value": video.shape[1] / dt_s, "unit": UNIT, "n_gpus": world, "windows": n_win, "frames": int(video.shape[1]),
+                "seconds": dt_s, "higher_is_better": True, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"{n_win} windows x {cl} frames at {W}x{H}, {N_DDIM} DDIM steps, host in -> host out; "
+                                       "a 30 s clip is 47 windows (750 frames padded to 752)", **config},
+                "ms_per_window_by_phase": {k: round(v, 2) for k, v in phases.items()},
+                "video_finite": bool(torch.isfinite(video).all())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        eng.graph = None
+        torch.cuda.synchronize()
+        if eng.arena is not None:
+            eng.arena.close()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -157,6 +239,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=64, help="latent side (64 = 512x512)")
     ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"], help="storage / tensor-core input type (configs[3]: bf16)")
+    ap.add_argument("--windows", type=int, default=0, metavar="N",
+                    help="BASELINE.json configs[4]: end-to-end frames/s of N sliding 16-frame windows through the whole "
+                         "pipeline (VAE, ReferenceNet, conditioning, denoising, decode, motion-frame hand-off), host to host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print a per-op time table of one eager forward")
@@ -168,8 +254,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, Wm = args.steps, max(args.warmup, 0)
+    which = {64: "configs[1]", 96: "configs[3]"}.get(args.size, "non-standard size")
     config = {"workload": f"{args.size * 8}x{args.size * 8}, {args.frames}-frame window, CFG batch 2, "
-                          f"{N_DDIM}-step DDIM (configs[1])", "latent": [2, 4, args.frames, args.size, args.size],
+                          f"{N_DDIM}-step DDIM ({which})", "latent": [2, 4, args.frames, args.size, args.size],
               "parallelism": f"frame-shard (both CFG halves per rank) over {world} rank(s)",
               "l2": "per-step working set >> 126 MB L2, no explicit flush"}
 
@@ -202,7 +289,9 @@ def main():
 
     peaks = load_peaks()
     cfg = UNetConfig()
-    dt = torch.float16
+    dt = torch.float16 if args.dtype == "f16" else torch.bfloat16
+    if args.windows > 0:
+        return run_clip(args, rank, world, dev, dt, config)
     from hallo_b200.synth import host_threads
     torch.set_num_threads(max(1, host_threads() // world))
     try:
@@ -469,7 +558,7 @@ def main():
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": config, "clocks": clk,
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "window_setup_ms": setup_ms,
