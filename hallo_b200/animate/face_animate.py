@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from ..models.mutual_self_attention import ReferenceAttentionControl
+from ..scheduler import coef_table_of
 
 
 @dataclass
@@ -193,7 +194,7 @@ class FaceAnimatePipeline:
         eng.begin_window(encoder_hidden_states=ehs, audio_embedding=audio, mask_cond_fea=static["mask_cond"],
                          full_mask=static["full"], face_mask=static["face"], lip_mask=static["lip"],
                          motion_scale=motion_scale, banks=unet._banks)
-        eng.set_schedule(timesteps.tolist(), self.scheduler.coef_table(), guidance_scale)
+        eng.set_schedule(timesteps.tolist(), coef_table_of(self.scheduler), guidance_scale)
         frames = list(eng.shard.frames)
         eng.latents.copy_(latents[:, :, frames].float())
         if self.use_cuda_graph and callback is None and eng.graph is None:

@@ -97,3 +97,27 @@ class DDIMScheduler:
             a_p = self.alphas_cumprod[prev].double() if prev >= 0 else self.final_alpha_cumprod.double()
             rows.append([float(a_t.sqrt()), float((1 - a_t).sqrt()), float(a_p.sqrt()), float((1 - a_p).sqrt())])
         return torch.tensor(rows, dtype=torch.float32)
+
+
+def coef_table_of(sched) -> torch.Tensor:
+    """The [n_steps, 4] table for ANY DDIM-style scheduler object that has run set_timesteps: hallo_b200's own class,
+    or diffusers.DDIMScheduler as the unmodified scripts/inference.py constructs it (:186-193) -- read through the
+    attributes diffusers exposes (alphas_cumprod, final_alpha_cumprod, timesteps, config.num_train_timesteps,
+    config.prediction_type)."""
+    if hasattr(sched, "coef_table"):
+        return sched.coef_table()
+    cfg = getattr(sched, "config", None)
+    pred = getattr(cfg, "prediction_type", None) if cfg is not None else None
+    if pred is None and isinstance(cfg, dict):
+        pred = cfg.get("prediction_type")
+    if pred not in (None, "v_prediction"):
+        raise NotImplementedError(f"the engine's DDIM update is the v-prediction form the reference ships, got {pred!r}")
+    T = int(cfg["num_train_timesteps"] if isinstance(cfg, dict) else getattr(cfg, "num_train_timesteps"))
+    n = int(sched.num_inference_steps)
+    rows = []
+    for t in [int(x) for x in sched.timesteps]:
+        prev = t - T // n
+        a_t = sched.alphas_cumprod[t].double()
+        a_p = sched.alphas_cumprod[prev].double() if prev >= 0 else torch.as_tensor(sched.final_alpha_cumprod).double()
+        rows.append([float(a_t.sqrt()), float((1 - a_t).sqrt()), float(a_p.sqrt()), float((1 - a_p).sqrt())])
+    return torch.tensor(rows, dtype=torch.float32)

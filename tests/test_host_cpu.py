@@ -235,6 +235,13 @@ def test_scheduler_step_matches_oracle_ddim():
         x = mine
     with pytest.raises(NotImplementedError):
         s.step(v, 24, x, eta=0.5)
+    # a diffusers-style scheduler object (attributes only, no coef_table): same table through coef_table_of
+    from types import SimpleNamespace
+    from hallo_b200.scheduler import coef_table_of
+    fake = SimpleNamespace(config=SimpleNamespace(num_train_timesteps=1000, prediction_type="v_prediction"),
+                           num_inference_steps=40, timesteps=s.timesteps, alphas_cumprod=s.alphas_cumprod,
+                           final_alpha_cumprod=s.final_alpha_cumprod)
+    assert torch.equal(coef_table_of(fake), c) and torch.equal(coef_table_of(s), c)
 
 
 def test_hallo_overlay_package_resolves_hot_path_to_b200_and_rest_to_reference():
