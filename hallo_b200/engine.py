@@ -260,7 +260,14 @@ class DenoiseEngine:
         self.me = sh.rank_in_group
         if sh.group_size > 1 and sh.exchange == "peer":
             from .peer import PeerArena
-            self.arena = PeerArena(regions, sh.group, sh.rank_in_group, sh.group_size, self.dev)
+            try:
+                # PeerArena agrees on success across the ranks: either every rank gets a mapped arena or every rank raises
+                self.arena = PeerArena(regions, sh.group, sh.rank_in_group, sh.group_size, self.dev)
+            except RuntimeError as e:                    # e.g. CUDA IPC not permitted between these processes
+                self.arena = None
+                sh.exchange = "nccl"
+                import sys
+                print(f"# hallo_b200: {e}; every rank uses the NCCL all-to-all exchange instead", file=sys.stderr)
         self._px_regions = dict(regions)
 
     def _x18(self, name: str, rows: int, C: int) -> torch.Tensor:

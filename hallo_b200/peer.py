@@ -38,25 +38,42 @@ class PeerArena:
             off += nbytes
         self.nbytes = (off + 1023) // 1024 * 1024
         h = lib.load()
-        base = C.c_void_p()
-        lib.check(h.hallo_b200_peer_alloc(C.c_int64(self.nbytes), C.byref(base)), "peer_alloc")
-        self.local_base = int(base.value)
-        handle = (C.c_ubyte * 64)()
-        lib.check(h.hallo_b200_peer_export(C.c_void_p(self.local_base), handle), "peer_export")
-        mine = bytes(handle)
+        # Every rank runs the SAME sequence of collectives whatever fails locally; the verdict is agreed with a MIN
+        # all-reduce, so either all ranks own a fully mapped arena or all of them raise.
+        self.local_base, self.bases, self._opened, self._bytes = 0, [], [], None
+        err = None
+        mine = b""
+        try:
+            base = C.c_void_p()
+            lib.check(h.hallo_b200_peer_alloc(C.c_int64(self.nbytes), C.byref(base)), "peer_alloc")
+            self.local_base = int(base.value)
+            handle = (C.c_ubyte * 64)()
+            lib.check(h.hallo_b200_peer_export(C.c_void_p(self.local_base), handle), "peer_export")
+            mine = bytes(handle)
+        except Exception as e:
+            err = e
         handles: List[bytes] = [b""] * world
         dist.all_gather_object(handles, mine, group=group)
-        self.bases: List[int] = []
-        self._opened: List[int] = []
-        for r in range(world):
-            if r == rank:
-                self.bases.append(self.local_base)
-                continue
-            buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-            p = C.c_void_p()
-            lib.check(h.hallo_b200_peer_open(buf, C.byref(p)), f"peer_open(rank {r})")
-            self.bases.append(int(p.value))
-            self._opened.append(int(p.value))
+        if err is None and all(len(x) == 64 for x in handles):
+            try:
+                for r in range(world):
+                    if r == rank:
+                        self.bases.append(self.local_base)
+                        continue
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    p = C.c_void_p()
+                    lib.check(h.hallo_b200_peer_open(buf, C.byref(p)), f"peer_open(rank {r})")
+                    self.bases.append(int(p.value))
+                    self._opened.append(int(p.value))
+            except Exception as e:
+                err = e
+        elif err is None:
+            err = RuntimeError("another rank could not export its exchange buffer")
+        ok = torch.tensor([0 if err is not None else 1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory arena unavailable: {err if err is not None else 'failed on another rank'}")
         self._mem = _DevMem(self.local_base, self.nbytes)
         self._bytes = torch.as_tensor(self._mem, device=device)           # uint8 view of the local allocation
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
