@@ -15,3 +15,5 @@ $N -k regex:layernorm -s 2 -c 1 -o gpurun_out/r2_prof_ln -f python tools/prof_au
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_one_step.csv \
     python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline > gpurun_out/r2_ncu_bench.log 2>&1
 ls -la gpurun_out/r2_prof_*.ncu-rep gpurun_out/r2_launches_one_step.csv
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_one_step_shard8.csv \
+    python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --emulate-shard 8 > gpurun_out/r2_ncu_bench_shard8.log 2>&1
