@@ -321,3 +321,47 @@ def test_vae_architecture_contract():
     assert tuple(z.shape) == (2, 4, 4, 4) and tuple(v.decode(z).sample.shape) == (2, 3, 32, 32)
     # per-sample independence (what lets the driver encode the source image once and decode frames in chunks)
     assert torch.allclose(v.encode(x[:1]).latent_dist.mean, z[:1], atol=1e-5)
+
+
+def test_from_pretrained_2d_on_a_synthetic_checkpoint(tmp_path):
+    """UNet3DConditionModel.from_pretrained_2d (hallo/models/unet_3d.py:717-839, scripts/inference.py:198-205) on a tiny
+    SD-style directory: <base>/unet/config.json + 2-D weights, an AnimateDiff-style motion checkpoint, non-strict load,
+    shape-mismatched tensors silently keep the model's own initialisation (:824-830)."""
+    import json
+    from hallo_b200.models.unet_3d import UNet3DConditionModel
+    from hallo_b200.spec import HALLO_UNET_KWARGS, UNetConfig, param_spec, param_spec_2d
+    base = tmp_path / "sd"
+    (base / "unet").mkdir(parents=True)
+    cfg_json = dict(_class_name="UNet2DConditionModel", _diffusers_version="0.6.0", sample_size=8, in_channels=4, out_channels=4,
+                    center_input_sample=False, flip_sin_to_cos=True, freq_shift=0,
+                    down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"],
+                    up_block_types=["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3, block_out_channels=[32, 64, 128, 128],
+                    layers_per_block=2, downsample_padding=1, mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32,
+                    norm_eps=1e-5, cross_attention_dim=768, attention_head_dim=8)
+    json.dump(cfg_json, open(base / "unet" / "config.json", "w"))
+    arch = UNetConfig(block_out_channels=(32, 64, 128, 128))
+    g = torch.Generator().manual_seed(0)
+    sd2d = {k: torch.randn(shape, generator=g) for k, shape, _ in param_spec_2d(arch)}
+    sd2d["conv_norm_out.weight"] = torch.randn(32, generator=g)           # SD checkpoints carry the output head too
+    sd2d["conv_in.weight"] = torch.randn(32, 9, 3, 3, generator=g)        # wrong shape on purpose (4 -> 9 input channels)
+    torch.save(sd2d, base / "unet" / "diffusion_pytorch_model.bin")
+    motion = {k: torch.randn(shape, generator=g) for k, shape, kind in param_spec(arch)
+              if "motion_modules" in k and kind != "pe"}
+    torch.save(motion, tmp_path / "mm.ckpt")
+    m = UNet3DConditionModel.from_pretrained_2d(str(base), str(tmp_path / "mm.ckpt"), subfolder="unet",
+                                                unet_additional_kwargs=dict(HALLO_UNET_KWARGS), use_landmark=False)
+    own = m.state_dict()
+    assert len(own) == len(param_spec(arch))
+    k2 = "down_blocks.1.attentions.0.transformer_blocks.0.attn1.to_q.weight"
+    km = "up_blocks.2.motion_modules.1.temporal_transformer.proj_in.weight"
+    assert torch.equal(own[k2], sd2d[k2]) and torch.equal(own[km], motion[km])
+    assert torch.equal(own["conv_norm_out.weight"], sd2d["conv_norm_out.weight"])
+    assert own["conv_in.weight"].shape == (32, 4, 3, 3)                   # mismatched tensor: own init kept, no error
+    ka = "mid_block.audio_modules.0.transformer_blocks.0.attn2_1.to_k.weight"
+    assert ka in own and ka not in sd2d                                   # absent keys: non-strict load
+    with pytest.raises(RuntimeError):
+        UNet3DConditionModel.from_pretrained_2d(str(tmp_path / "nope"), str(tmp_path / "mm.ckpt"), subfolder="unet")
+    with pytest.raises(RuntimeError):
+        (tmp_path / "mm.bad").write_bytes(b"x")
+        UNet3DConditionModel.from_pretrained_2d(str(base), str(tmp_path / "mm.bad"), subfolder="unet",
+                                                unet_additional_kwargs=dict(HALLO_UNET_KWARGS), use_landmark=False)
