@@ -31,14 +31,14 @@ constexpr int kAttn2Threads = 384;   // warpgroup 0: TMA / MMA / TMEM-alloc / id
 // the launch bound (65536 / 2 / 320 -> 96 registers per thread), which the 64-column S row fits
 constexpr int kAttn2ThreadsOcc2 = 320;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 / 6-9 softmax of tile A / B
 
-template <int D, int BN>
+template <int D, int BN, int NSTG = 2>
 struct Attn2Cfg {
   static constexpr int kChunks = (D + 63) / 64;
   static constexpr int kKSteps = (D + 15) / 16;
   static constexpr int kDv = ((D + 15) / 16) * 16;
   static constexpr int kQBytes = kChunks * 128 * 128;     // one Q tile
   static constexpr int kKVBytes = kChunks * BN * 128;
-  static constexpr int kStages = 2;
+  static constexpr int kStages = NSTG;          // K / V ring depth (shared by both tiles of the CTA)
   static constexpr int kOffK = 2 * kQBytes;
   static constexpr int kOffV = kOffK + kStages * kKVBytes;
   static constexpr int kOffBar = kOffV + kStages * kKVBytes;
@@ -51,12 +51,12 @@ struct Attn2Cfg {
 };
 
 // POLY: every POLY-th exponential of a row goes to the FMA pipe (exp2_poly) instead of the SFU; 0 = all on the SFU
-template <typename T, int D, int BN, int POLY, int MINB = 1>
+template <typename T, int D, int BN, int POLY, int MINB = 1, int NSTG = 2>
 __global__ void __launch_bounds__(MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2, MINB)
 attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                 const __grid_constant__ CUtensorMap tmV1, const AttnDev p) {
-  using CF = Attn2Cfg<D, BN>;
+  using CF = Attn2Cfg<D, BN, NSTG>;
   constexpr int STAGES = CF::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -326,9 +326,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <typename T, int D, int BN, int POLY, int MINB = 1>
+template <typename T, int D, int BN, int POLY, int MINB = 1, int NSTG = 2>
 static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
-  using CF = Attn2Cfg<D, BN>;
+  using CF = Attn2Cfg<D, BN, NSTG>;
   static_assert(CF::kTotal <= 232448, "attention v2 smem budget");
   CUtensorMap tmQ, tmK0, tmV0, tmK1, tmV1;
   int rc;
@@ -352,7 +352,7 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   d.O = q->O;
   d.ldo = q->ldo;
   d.scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  auto kern = attn2_tc_kernel<T, D, BN, POLY, MINB>;
+  auto kern = attn2_tc_kernel<T, D, BN, POLY, MINB, NSTG>;
   static bool attr_set = false;
   if (!attr_set) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kTotal));

@@ -9,6 +9,12 @@ timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-op
 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --size 96 --dtype bf16 > gpurun_out/r2d_bench_768_bf16.json 2> gpurun_out/r2d_bench_768_bf16.log
 timeout 900 python bench.py --windows 2 > gpurun_out/r2d_clip_2win.json 2> gpurun_out/r2d_clip_2win.log
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --emulate-shard 8 --profile-ops > gpurun_out/r2d_bench_shard8.json 2> gpurun_out/r2d_bench_shard8_ops.log
+HALLO_B200_ATTN_OCC2=2 timeout 300 python -m pytest tests/test_attention_gpu.py -q -m gpu -x -p no:cacheprovider > gpurun_out/r2d_attn_stg4_tests.log 2>&1
+echo "attn occ2=2 (4-stage ring) tests exit $?" >> gpurun_out/r2d_summary.txt
+timeout 300 python tools/kbench.py attn gemm > gpurun_out/r2d_kbench.log 2>&1
+HALLO_B200_ATTN_OCC2=2 timeout 300 python tools/kbench.py attn > gpurun_out/r2d_kbench_attn_stg4.log 2>&1
+grep -h "L4096" gpurun_out/r2d_kbench.log gpurun_out/r2d_kbench_attn_stg4.log >> gpurun_out/r2d_summary.txt
+grep -h "geglu" -A1 gpurun_out/r2d_kbench.log >> gpurun_out/r2d_summary.txt
 for f in gpurun_out/r2d_bench.json gpurun_out/r2d_bench_768_bf16.json gpurun_out/r2d_bench_shard8.json; do
 python - $f <<'PY' >> gpurun_out/r2d_summary.txt
 import json, sys
