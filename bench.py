@@ -448,7 +448,10 @@ def main():
     shard_err = None
     if world > 1:
         from hallo_b200.dist import sharded_vs_unsharded
-        shard_err = sharded_vs_unsharded(eng, inp, steps=2, use_graph=eng.graph is not None)
+        try:
+            shard_err = sharded_vs_unsharded(eng, inp, steps=2, use_graph=eng.graph is not None)
+        except Exception as e:                               # never costs the bench line; the failure is reported in it
+            shard_err = f"check failed: {type(e).__name__}: {e}"
 
     def orderly_exit():
         """Graphs first (a live graph holding NCCL work is what hung destroy_process_group in round 1), then the peer
