@@ -44,8 +44,9 @@ class Shard:
     group_size: int = 1
     rank_in_group: int = 0
     exchange: str = "peer"                  # "peer": kernels store into peer-mapped buffers; "nccl": all_to_all_single
-    emulate_group: int = 1                  # profiling aid (bench.py --emulate-shard): single GPU running ONE rank's
-                                            # shapes of an R-rank job; the peers' rows are copies of the local ones
+    emulate_group: int = 1                  # PROFILING AID ONLY (bench.py --emulate-shard): single GPU running ONE rank's
+                                            # kernel shapes of an R-rank job; the peers' rows are stand-in copies of the
+                                            # local ones, so the numbers it produces are not a valid denoising result
 
 
 class PackedWeights:

@@ -97,52 +97,45 @@ def test_unet_forward_run_to_run_reproducibility(model):
     assert err < 2e-3
 
 
-def test_pixel_transposed_motion_modules_on_one_gpu(model):
+@pytest.mark.parametrize("R", [2, 4])
+def test_frame_sharded_window_on_one_gpu(model, monkeypatch, R):
     """The frame-sharded path (engine._motion_px: frame <-> pixel swap around every motion module) without a second GPU:
-    with a window whose frames repeat with period fl AND the temporal positional encoding zeroed (so that temporal
-    attention cannot tell the repeats apart and they stay identical through every layer), the rows the other ranks
-    would send are copies of the local ones -- exactly what Shard(emulate_group=R) substitutes -- so rank 0's emulated
-    shard must reproduce frames [0, fl) of the unsharded forward.  Checks the x18 layout, the pixel-slice bookkeeping,
-    the local-frame window slicing and the row order of the swaps; the positional indices and the peer-memory
-    transport itself are covered by tests/test_multigpu_gpu.py."""
+    R ranks run as threads of this process on the same device -- every rank a real DenoiseEngine with its own buffers and
+    the real kernels -- and torch.distributed.all_to_all_single is replaced by an in-process exchange
+    (conftest.ThreadGroup), i.e. the engine's exchange="nccl" code path.  The gathered output must equal the unsharded
+    forward; every kernel on the path is deterministic and row-independent, so the match is (nearly) exact.  The
+    peer-memory transport (fused scatter stores + flag barriers) is tests/test_multigpu_gpu.py."""
+    from conftest import ThreadGroup
     from hallo_b200.dist import window_inputs_to_device
     from hallo_b200.engine import DenoiseEngine, Shard
     from hallo_b200.spec import UNetConfig
     from hallo_b200.synth import synth_inputs
     m, _ = model
     dev = _dev()
-    f, R, size = 16, 4, 32
+    f, size = 16, 32
     fl = f // R
     inp = synth_inputs(UNetConfig(), size, size, f, seed=31, timestep=600, motion_scale=(1.0, 0.8, 1.2))
-    per = lambda t, dim: t.index_select(dim, torch.arange(f) % fl)          # frames repeat with period fl
-    inp["sample"] = per(inp["sample"], 2)
-    inp["audio_embedding"] = per(inp["audio_embedding"], 1)
-    inp["mask_cond_fea"] = per(inp["mask_cond_fea"], 2)
-    rows = torch.cat([b * f + (torch.arange(f) % fl) for b in (0, 1)])
-    for k in ("full_mask", "face_mask", "lip_mask"):
-        inp[k] = [t[rows] for t in inp[k]]
     W = m._weights()
-    pe_keys = [k for k in W.t if k.endswith(".pe")]
-    saved = {k: W.t[k].clone() for k in pe_keys}
-    try:
-        for k in pe_keys:
-            W.t[k].zero_()
-        full = DenoiseEngine(W, size, size, f)
-        full.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
-        full.set_timestep(inp["timestep"])
-        ref_all = full.forward_only(inp["sample"].float())
-        assert rel_l2(ref_all[:, :, fl:2 * fl], ref_all[:, :, :fl]) < 1e-6        # the premise: repeats stay identical
-        ref = ref_all[:, :, :fl]
-        shard = DenoiseEngine(W, size, size, f, Shard(frames=tuple(range(fl)), emulate_group=R))
-        shard.begin_window(**window_inputs_to_device(inp, dev, torch.float16))
-        shard.set_timestep(inp["timestep"])
-        out = shard.forward_only(inp["sample"][:, :, :fl].float())
+    win = window_inputs_to_device(inp, dev, torch.float16)
+    full = DenoiseEngine(W, size, size, f)
+    full.begin_window(**win)
+    full.set_timestep(inp["timestep"])
+    ref = full.forward_only(inp["sample"].float()).clone()
+    grp = ThreadGroup(R, monkeypatch)
+
+    def rank_fn(r):
+        torch.cuda.set_device(dev)
+        frames = tuple(range(r * fl, (r + 1) * fl))
+        eng = DenoiseEngine(W, size, size, f, Shard(frames=frames, group=grp, group_size=R, rank_in_group=r, exchange="nccl"))
+        eng.begin_window(**win)
+        eng.set_timestep(inp["timestep"])
+        out = eng.forward_only(inp["sample"][:, :, list(frames)].float()).clone()
         torch.cuda.synchronize()
-    finally:
-        for k in pe_keys:
-            W.t[k].copy_(saved[k])
-    err = rel_l2(out, ref)
-    print(f"emulated rank 0 of {R} vs unsharded frames [0, {fl}): rel L2 = {err:.3e}")
+        return out
+
+    got = torch.cat(grp.run(rank_fn), dim=2)
+    err = rel_l2(got, ref)
+    print(f"{R} thread-ranks on one GPU vs unsharded: rel L2 = {err:.3e} (bitwise equal: {torch.equal(got, ref)})")
     assert err < 2e-3
 
 
