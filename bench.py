@@ -507,7 +507,7 @@ def main():
                 "ms_per_launch": attn_ms, "algorithmic_flops_per_launch": attn_flops,
                 "whole_step": {"achieved": fl["total"] * world / world / (ms_step * 1e-3) / 1e12 / world,
                                "peak": peaks["sustained"], "frac": fl["total"] / (ms_step * 1e-3) / 1e12 / world / peaks["sustained"],
-                               "unit": "TFLOP/s per GPU (48.44 TFLOP algorithmic per forward)"}}
+                               "unit": f"TFLOP/s per GPU ({fl['total'] / 1e12:.2f} TFLOP algorithmic per forward)"}}
 
     if prof_saved is not None:
         agg, byname = {}, {}

@@ -410,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // (value, gate) pairs: 32 accumulator columns -> 16 outputs = chunks 2*(u&1), 2*(u&1)+1 of the panel row
           float o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_poly(v[2 * j + 1]) * rs;
+          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint32_t cell = sbuf_u32 + row_off + ((((uint32_t)((u & 1) * 2 + c)) ^ row_sw) << 4);
@@ -613,7 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ocol0 = col0 >> 1;
             float o[CW / 2];
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) o[j] = v[2 * j] * gelu_poly(v[2 * j + 1]) * rs;
+            for (int j = 0; j < CW / 2; ++j) o[j] = v[2 * j] * gelu_fast(v[2 * j + 1]) * rs;
 #pragma unroll
             for (int j = 0; j < CW / 2; j += 8) {
               if (resid != nullptr) {

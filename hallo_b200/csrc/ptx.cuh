@@ -443,26 +443,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erfx = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erfx);
 }
-// erf-GELU with NO special-function-unit work: erf(z) ~ z * P(z^2) on [0, 3] (degree-7 minimax in z^2, max abs error
-// 8.4e-5 -- below half-precision rounding of the activations), clamped to 1 beyond.  The GEGLU epilogue evaluates one
-// GELU per output element: with gelu_fast that is 2 MUFU ops per element on a 16/clk/SM pipe -- 2048 clk per 128 x 256
-// tile against 2560 clk of MMA at K = 320 -- which made the K = 320 GEGLU GEMMs epilogue-bound.
-__device__ __forceinline__ float gelu_poly(float x) {
-  const float ax = fabsf(x);
-  const float zr = ax * 0.70710678118654752f;
-  const float z = fminf(zr, 3.0f);
-  const float s = z * z;
-  float p = -4.0553615576754964e-07f;
-  p = fmaf(p, s, 1.7159834897029214e-05f);
-  p = fmaf(p, s, -0.00031459543970413506f);
-  p = fmaf(p, s, 0.0033187109511345625f);
-  p = fmaf(p, s, -0.02268579974770546f);
-  p = fmaf(p, s, 0.10771782696247101f);
-  p = fmaf(p, s, -0.3732314109802246f);
-  p = fmaf(p, s, 1.127895712852478f);
-  const float e = (zr >= 3.0f) ? 1.0f : fminf(z * p, 1.0f);   // erf(|x| / sqrt 2); exactly 1 in the tail (1 - erf(3) = 2e-5)
-  return 0.5f * fmaf(ax, e, x);                    // 0.5 x (1 + sign(x) erf) = 0.5 (x + |x| erf)
-}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------
