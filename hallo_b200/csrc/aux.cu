@@ -849,8 +849,10 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
     const int cpg = C / G;
     const size_t slab = (size_t)HW * cpg * 2;
     // measured (profiles/r2_first_call_summary.txt): the one-launch kernel wins where the three launches are pure
-    // latency (levels 2-3, HW <= 256) and loses at HW >= 1024 (a CTA reads C/G-channel slivers of every pixel)
-    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024 && sc.seg == 0 && HW <= 256) {
+    // latency -- levels 2-3 (HW <= 256), and any norm of a sharded rank whose whole input is a few MB -- and loses on
+    // the 40-80 MB norms of levels 0-1 at 32 frames (a CTA reads C/G-channel slivers of every pixel: 1.9 -> 3.7 ms)
+    const bool small = HW <= 256 || (size_t)N * HW * C * 2 <= ((size_t)12 << 20);
+    if (hb::option(hb::OPT_GN_FUSED) != 0 && cpg % 2 == 0 && slab <= 96 * 1024 && sc.seg == 0 && small) {
       if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
       const int vw = (cpg % 8 == 0) ? 4 : ((cpg % 4 == 0) ? 2 : 1);     // channel pairs per access (16 / 8 / 4 bytes)
       HB_DISPATCH_T(dtype, {
