@@ -16,6 +16,13 @@ from typing import List, Tuple
 from .engine import Shard
 
 
+# "peer": the frame <-> pixel swap is fused into the producing kernels' stores over NVLink peer memory (the product path);
+# "nccl": the same swap as two all_to_all_single calls per motion module (A/B baseline and safe fallback).
+# The default flips to "peer" only on evidence: tests/test_multigpu_gpu.py green on real multi-GPU hardware
+# (profiles/r2e_*); until then a job that nobody has validated on >= 2 GPUs must not depend on it.
+DEFAULT_EXCHANGE = "nccl"
+
+
 def frame_groups(n_frames: int, groups: int) -> List[Tuple[int, ...]]:
     if groups < 1 or n_frames % groups != 0:
         raise ValueError(f"{n_frames} frames do not split into {groups} equal groups")
@@ -33,7 +40,7 @@ def plan_shard(rank: int, world: int, n_frames: int, exchange: str = None) -> Sh
     if world == 1:
         return Shard(halves=halves, frames=frames)
     import torch.distributed as dist
-    exchange = exchange or os.environ.get("HALLO_B200_EXCHANGE", "peer")
+    exchange = exchange or os.environ.get("HALLO_B200_EXCHANGE", DEFAULT_EXCHANGE)
     if exchange not in ("peer", "nccl"):
         raise ValueError(f"HALLO_B200_EXCHANGE must be 'peer' or 'nccl', got {exchange!r}")
     return Shard(halves=halves, frames=frames, group=dist.group.WORLD, group_size=world, rank_in_group=rank,
