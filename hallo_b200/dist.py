@@ -18,9 +18,9 @@ from .engine import Shard
 
 # "peer": the frame <-> pixel swap is fused into the producing kernels' stores over NVLink peer memory (the product path);
 # "nccl": the same swap as two all_to_all_single calls per motion module (A/B baseline and safe fallback).
-# The default flips to "peer" only on evidence: tests/test_multigpu_gpu.py green on real multi-GPU hardware
-# (profiles/r2e_*); until then a job that nobody has validated on >= 2 GPUs must not depend on it.
-DEFAULT_EXCHANGE = "nccl"
+# "peer" is the default on evidence: tests/test_multigpu_gpu.py green on 2 x B200 (sharded vs unsharded 5.5e-5, eagerly
+# and through the captured graph, both exchanges; profiles/r2e_summary.txt) and 1.04x faster than the NCCL variant.
+DEFAULT_EXCHANGE = "peer"
 
 
 def frame_groups(n_frames: int, groups: int) -> List[Tuple[int, ...]]:

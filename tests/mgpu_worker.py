@@ -54,5 +54,8 @@ torch.cuda.synchronize()
 if eng.arena is not None:
     eng.arena.close()
 dist.barrier()
+if sh.exchange == "nccl":      # a process that captured NCCL work into a CUDA graph cannot destroy its group promptly
+    sys.stdout.flush()
+    os._exit(0)
 dist.destroy_process_group()
 faulthandler.cancel_dump_traceback_later()
