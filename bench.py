@@ -227,6 +227,9 @@ def run_clip(args, rank, world, dev, dt, config):
         if eng.arena is not None:
             eng.arena.close()
         dist.barrier()
+        if eng.px and eng.arena is None:                 # NCCL work captured in the graph: see orderly_exit() in main()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
