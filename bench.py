@@ -248,6 +248,9 @@ def main():
                          "pipeline (VAE, ReferenceNet, conditioning, denoising, decode, motion-frame hand-off), host to host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="wrap ONE eager denoising step in cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`: "
+                         "the launch list then holds exactly the step's kernels, not the set-up's)")
     ap.add_argument("--profile-ops", action="store_true", help="print a per-op time table of one eager forward")
     ap.add_argument("--emulate-shard", type=int, default=0, metavar="R",
                     help="single GPU: run the workload of ONE rank of an R-rank job (cond half, first frame group, no "
@@ -357,6 +360,15 @@ def main():
     eng.set_schedule(sch.timesteps.tolist(), sch.coef_table(), 3.5)
     eng.latents.copy_(lat_host.to(dev))
     lib.launch_count(reset=True)
+    if args.profiler_range:
+        eng.step()                                   # warm-up (allocates every buffer)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eng.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiler_range": "one eager denoising step", "launches": lib.launch_count(reset=True) // 2}))
+        return
     if args.no_graph:
         eng.step()
         launches_per_step = lib.launch_count(reset=True)
