@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 call 7 (8 GPUs): 8-rank parity (peer memory), bench at N = 8 and N = 4, configs[3] at 8 GPUs, a clip at 8 GPUs.
+# Round-2 call 7 (8 GPUs): 8-rank parity (peer memory), bench at N = 8, configs[3] at 8 GPUs, a clip at 8 GPUs.
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 600 python -m pytest tests/test_multigpu_gpu.py -q -m gpu -p no:cacheprovider -rA -s -k peer > gpurun_out/r2g_tests_mgpu8.log 2>&1
@@ -7,13 +7,11 @@ echo "8-rank parity test exit $?" | tee gpurun_out/r2g_summary.txt
 grep -E "world|passed|failed|Error" gpurun_out/r2g_tests_mgpu8.log | tail -5 >> gpurun_out/r2g_summary.txt
 timeout 420 $T --nproc-per-node 8 --master-port 29551 bench.py --gpus 8 --steps 20 --warmup 5 --profile-ops > gpurun_out/r2g_bench_n8.json 2> gpurun_out/r2g_bench_n8_ops.log
 echo "bench n8 exit $?" | tee -a gpurun_out/r2g_summary.txt
-timeout 420 $T --nproc-per-node 4 --master-port 29552 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2g_bench_n4.json 2> gpurun_out/r2g_bench_n4.log
-echo "bench n4 exit $?" | tee -a gpurun_out/r2g_summary.txt
 timeout 420 $T --nproc-per-node 8 --master-port 29553 bench.py --gpus 8 --steps 10 --warmup 3 --size 96 --dtype bf16 > gpurun_out/r2g_bench_n8_768_bf16.json 2> gpurun_out/r2g_bench_n8_768_bf16.log
 echo "bench n8 768 bf16 exit $?" | tee -a gpurun_out/r2g_summary.txt
-timeout 420 $T --nproc-per-node 8 --master-port 29554 bench.py --gpus 8 --windows 4 > gpurun_out/r2g_clip_n8.json 2> gpurun_out/r2g_clip_n8.log
+timeout 420 $T --nproc-per-node 8 --master-port 29554 bench.py --gpus 8 --windows 3 > gpurun_out/r2g_clip_n8.json 2> gpurun_out/r2g_clip_n8.log
 echo "clip n8 exit $?" | tee -a gpurun_out/r2g_summary.txt
-for f in gpurun_out/r2g_bench_n8.json gpurun_out/r2g_bench_n4.json gpurun_out/r2g_bench_n8_768_bf16.json; do
+for f in gpurun_out/r2g_bench_n8.json gpurun_out/r2g_bench_n8_768_bf16.json; do
 python - $f <<'PY' >> gpurun_out/r2g_summary.txt
 import json, sys
 try:
