@@ -164,15 +164,22 @@ def run_clip(args, rank, world, dev, dt, config):
     from hallo_b200.models.vae import AutoencoderKL
     from hallo_b200.scheduler import DDIMScheduler
     from hallo_b200.spec import HALLO_UNET_KWARGS, SD15_UNET_CONFIG, UNetConfig
-    from hallo_b200.synth import mask_levels, synth_audio_proj_state_dict, synth_state_dict, synth_state_dict_2d
+    from hallo_b200.synth import mask_levels, synth_audio_proj_state_dict
     cfg = UNetConfig()
     H = W = args.size * 8
     cl = args.frames
     torch.manual_seed(0)
-    unet = UNet3DConditionModel.from_config(SD15_UNET_CONFIG, **HALLO_UNET_KWARGS)
-    unet.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
-    refnet = UNet2DConditionModel.from_config(SD15_UNET_CONFIG)
-    refnet.load_state_dict(synth_state_dict_2d(cfg), strict=True)
+    # parameters are created uninitialised on the device and filled from device-drawn random-init weights: nothing of the
+    # 1.5 G + 0.86 G parameters is drawn or held on the host (8 ranks share one box)
+    from hallo_b200.models.unet_3d import empty_weights
+    from hallo_b200.spec import param_spec_2d
+    from hallo_b200.synth import synth_state_dict_device
+    with empty_weights(dev, dt):
+        unet = UNet3DConditionModel.from_config(SD15_UNET_CONFIG, **HALLO_UNET_KWARGS)
+        refnet = UNet2DConditionModel.from_config(SD15_UNET_CONFIG)
+    unet.load_state_dict(synth_state_dict_device(cfg, dev, seed=0), strict=True)
+    refnet.load_state_dict(synth_state_dict_device(cfg, dev, seed=1, spec=param_spec_2d(cfg)), strict=True)
+    torch.cuda.empty_cache()
     vae = AutoencoderKL().to(memory_format=torch.channels_last)
     fl_ = FaceLocator(conditioning_embedding_channels=320)
     torch.nn.init.normal_(fl_.conv_out.weight, std=0.02)                      # de-zeroed so the branch is live

@@ -19,7 +19,7 @@ from torch import nn
 
 from ..refnet import ReferenceNetEngine, ReferenceNetWeights
 from ..spec import SD15_UNET_CONFIG, UNetConfig, param_spec_2d
-from .unet_3d import _attach
+from .unet_3d import _attach, _new_param
 
 
 @dataclass
@@ -53,15 +53,7 @@ class UNet2DConditionModel(nn.Module):
                                cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups, norm_eps=norm_eps)
         g = torch.Generator().manual_seed(1)
         for key, shape, kind in param_spec_2d(self.arch):
-            if kind == "w":
-                fan_in = 1
-                for s in shape[1:]:
-                    fan_in *= s
-                t = torch.empty(shape).uniform_(-1, 1, generator=g) * (fan_in ** -0.5)
-            elif kind == "norm_w":
-                t = torch.ones(shape)
-            else:
-                t = torch.zeros(shape)
+            t = _new_param(shape, kind, g)
             _attach(self, key, t, buffer=False)
         self.gradient_checkpointing = False
         self._packed: Optional[ReferenceNetWeights] = None

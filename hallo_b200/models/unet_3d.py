@@ -31,6 +31,40 @@ class _Node(nn.Module):
     """Pure parameter container; the tree only exists to reproduce the reference's state-dict keys."""
 
 
+# Construction target of the parameter tensors.  Default: initialised fp32 tensors on the host (what `from_config` of the
+# reference produces).  `with empty_weights(device, dtype):` creates them uninitialised, directly on the device, for callers
+# that load a state dict right after (bench.py: 8 ranks x 1.5 G parameters would otherwise be drawn and held on the host).
+_INIT = {"device": None, "dtype": None, "empty": False}
+
+
+class empty_weights:
+    def __init__(self, device, dtype):
+        self.new = {"device": device, "dtype": dtype, "empty": True}
+
+    def __enter__(self):
+        self.old = dict(_INIT)
+        _INIT.update(self.new)
+
+    def __exit__(self, *exc):
+        _INIT.update(self.old)
+        return False
+
+
+def _new_param(shape, kind, g):
+    """One parameter tensor of the given kind (param_spec): reference-like default initialisation, or uninitialised
+    device storage inside `empty_weights`."""
+    if _INIT["empty"]:
+        return torch.empty(shape, device=_INIT["device"], dtype=_INIT["dtype"])
+    if kind == "w":
+        fan_in = 1
+        for s_ in shape[1:]:
+            fan_in *= s_
+        return torch.empty(shape).uniform_(-1, 1, generator=g) * (fan_in ** -0.5)
+    if kind == "norm_w":
+        return torch.ones(shape)
+    return torch.zeros(shape)          # zero_w (reference zero-initialises), biases, norm biases
+
+
 def _attach(root: nn.Module, key: str, tensor: torch.Tensor, buffer: bool):
     parts = key.split(".")
     m = root
@@ -95,15 +129,7 @@ class UNet3DConditionModel(nn.Module):
             if kind == "pe":
                 _attach(self, key, sinusoid_pe(shape[1], shape[2]), buffer=True)
                 continue
-            if kind == "w":
-                fan_in = 1
-                for s in shape[1:]:
-                    fan_in *= s
-                t = torch.empty(shape).uniform_(-1, 1, generator=g) * (fan_in ** -0.5)
-            elif kind == "norm_w":
-                t = torch.ones(shape)
-            else:                         # zero_w (reference zero-initialises), biases, norm biases
-                t = torch.zeros(shape)
+            t = _new_param(shape, kind, g)
             _attach(self, key, t, buffer=False)
         self.gradient_checkpointing = False
         self._banks: Dict[str, torch.Tensor] = {}

@@ -55,13 +55,13 @@ def synth_state_dict(cfg: UNetConfig, seed: int = 0, dtype=torch.float32,
     return sd
 
 
-def synth_state_dict_device(cfg: UNetConfig, device, seed: int = 0) -> Dict[str, torch.Tensor]:
+def synth_state_dict_device(cfg: UNetConfig, device, seed: int = 0, spec=None) -> Dict[str, torch.Tensor]:
     """Same distributions as synth_state_dict but drawn directly on `device` from one seeded stream (about a
     second instead of ~15 s per process on the host).  Used by bench.py, where only "random-init weights of the
     architecture" matters; the parity tests keep the per-key CPU streams so that the oracle sees identical values."""
     torch.manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, kind in param_spec(cfg):
+    for key, shape, kind in (param_spec(cfg) if spec is None else spec):
         if kind == "pe":
             sd[key] = sinusoid_pe(shape[1], shape[2]).to(device)
         elif kind in ("w", "zero_w"):
