@@ -23,3 +23,6 @@ L="ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-star
 $L --log-file gpurun_out/r2_launches_one_step.csv python bench.py --profiler-range > gpurun_out/r2_ncu_bench.log 2>&1
 $L --log-file gpurun_out/r2_launches_one_step_shard8.csv python bench.py --profiler-range --emulate-shard 8 > gpurun_out/r2_ncu_bench_shard8.log 2>&1
 du -sh gpurun_out
+python __graft_entry__.py --smoke > gpurun_out/r2_smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/r2_smoke.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.log
+tail -3 gpurun_out/r2_smoke.log
