@@ -403,10 +403,11 @@ class DenoiseEngine:
                         ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
                                       n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
                                       fpb_in=nm, fpb_out=nm + fl, frame_off=0)
-        torch.cuda.current_stream().synchronize()
         if self.arena is not None:
-            import torch.distributed as dist
-            dist.barrier(group=sh.group)        # no rank starts stepping (and storing into peers) before all are set up
+            # ranks meet once per window on the device (flag barrier, stream-ordered, no host round trip): a peer's first
+            # scatter store of the new window cannot overtake this rank's window set-up
+            self.arena.barrier()
+        torch.cuda.current_stream().synchronize()
 
     def set_schedule(self, timesteps: Sequence[int], coef: torch.Tensor, guidance: float):
         """Per-window schedule.  The tables keep their device addresses (a captured graph reads them); the step count
