@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags pf, in
     const long long t0 = clock64();
     // signed distance: correct across the (theoretical) wrap of the 32-bit epoch
     while ((int)(ld_acquire_sys(mine) - e) < 0) {
-      if (clock64() - t0 > 4000000000LL) {     // ~2 s at 1.9 GHz: a peer died or fell out of step -- do not hang the GPU
+      if (clock64() - t0 > 40000000000LL) {    // ~20 s at 1.9 GHz: a peer died or fell out of step -- do not hang the GPU
         atomicExch(&g_hb_error, 0x70u | ((unsigned int)threadIdx.x << 8));
         break;
       }

@@ -274,7 +274,7 @@ int hallo_b200_peer_close(void* ptr);
  * zero-initialised; flags[me] is local, the others peer-mapped).  epoch: local device counter (uint32, starts 0),
  * incremented by every call -- kept on the device so that a captured CUDA graph replays correctly.  Everything the
  * calling stream wrote to peer memory before the barrier is visible to the peers' kernels after it.  A rank that
- * waits longer than ~2 s records HB_ERR_DEVICE_TRAP in the device error word instead of hanging the GPU. */
+ * waits longer than ~20 s records HB_ERR_DEVICE_TRAP in the device error word instead of hanging the GPU. */
 int hallo_b200_peer_barrier(void* const* flags /* host array of n device pointers */, int n, int me,
                             uint32_t* epoch, hb_stream_t stream);
 /* hallo_b200_groupnorm whose output rows are scattered by pixel: pixel p of (remapped) frame n_out goes to
