@@ -523,9 +523,9 @@ def main():
     achieved = attn_flops / (attn_ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        ns = json.load(open(os.path.join(ROOT, "profiles", "r1_attn_ncu_summary.json")))
-        if world == 1 and args.size == 64 and args.frames == 16:
-            traffic, traffic_src = ns["traffic_bytes"], "profiles/r1_attn_ncu_summary.json (ncu --set full, same shape)"
+        ns = [e for e in json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summaries.json"))) if e["name"] == "attn"][0]
+        if args.size == 64 and Bl == 32 and args.dtype == "f16":
+            traffic, traffic_src = ns["traffic_bytes"], "profiles/r2_ncu_summaries.json (ncu --set full, same kernel and shape)"
     except Exception:
         pass
     roofline = {"kernel": "attn2_tc_kernel<D=40> (spatial self-attention + in-kernel reference-KV concat, L0)",
