@@ -443,7 +443,14 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erfx = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erfx);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with one ex2.approx and one rcp.approx (the IEEE division of `x / (1 + exp(-x))` costs ~8 extra
+// instructions per element; GroupNorm-apply + SiLU was issue / SFU bound at 2.1 TB/s: profiles/r2_ncu_summaries.json)
+__device__ __forceinline__ float silu_f(float x) {
+  const float e = fast_exp2(-1.4426950408889634f * x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 // ------------------------------------------------------------------------------------------
 // warp-level tensor-core path (mma.sync m16n8k16, ldmatrix, cp.async): the small-problem kernels
