@@ -180,98 +180,38 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(&k_empty[0]);
     }
     __syncwarp();
-    if (p.dyn) {
-      // Dynamic order: the two query tiles of the CTA advance independently -- the MMA warp polls both p_full barriers
-      // and serves the tile whose P is ready, so one tile's softmax never waits behind the other's (the static order
-      // below couples them: 31 % of the softmax warps' samples sat on s_full, profiles/r2_ncu_attn_stalls.txt).
-      // Tiles can be at most STAGES - 1 steps apart (a K/V stage is recycled only after BOTH tiles have issued their
-      // MMA on it: the per-stage counters below), and every wait is a poll, so a lagging tile is never starved.
-      int jt[2] = {0, 0};
-      int pvc[STAGES], qkc[STAGES];
-#pragma unroll
-      for (int i = 0; i < STAGES; ++i) pvc[i] = qkc[i] = 0;
-      int t = 0, finished = 0;
-      long long t0 = clock64();
-      while (finished < 2) {
-        bool ready = false;
-        int j = 0, vs = 0, ks = 0;
-        bool more = false;
-        if (jt[t] < ntiles) {
-          j = jt[t];
-          more = (j + 1 < ntiles);
-          vs = j % STAGES;
-          ks = (j + 1) % STAGES;
-          ready = mbar_try_wait(&p_full[t], (uint32_t)(j & 1)) &&
-                  mbar_try_wait(&v_full[vs], (uint32_t)((j / STAGES) & 1)) &&
-                  (!more || mbar_try_wait(&k_full[ks], (uint32_t)(((j + 1) / STAGES) & 1)));
-          ready = __shfl_sync(0xffffffffu, ready ? 1 : 0, 0) != 0;
-        }
-        if (ready) {
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t vbase = sV + vs * CF::kKVBytes;
-#pragma unroll
-            for (int k = 0; k < BN / 16; ++k)
-              umma_f16_ts(o_col[t], s_col[t] + k * 8, make_desc_sw128(vbase + k * 2048, BN * 128, 1024), idesc_pv,
-                          (j | k) != 0);
-            if (++pvc[vs] == 2) {
-              pvc[vs] = 0;
-              umma_commit(&v_empty[vs]);
-            }
-            if (!more) {
-              umma_commit(&o_done[t]);
-            } else {
-              issue_qk(t, ks);
-              umma_commit(&s_full[t]);
-              if (++qkc[ks] == 2) {
-                qkc[ks] = 0;
-                umma_commit(&k_empty[ks]);
-              }
-            }
-          }
-          __syncwarp();
-          if (++jt[t] == ntiles) ++finished;
-          t0 = clock64();
-        } else if (clock64() - t0 > 4000000000LL) {
-          atomicExch(&g_hb_error, 0x86u | (blockIdx.x << 8));
-          __trap();
-        }
-        t ^= 1;
-      }
-    } else {
-      int kstage = 1 % STAGES, vstage = 0;
-      uint32_t kphase = (STAGES == 1) ? 1 : 0, vphase = 0;
+    int kstage = 1 % STAGES, vstage = 0;
+    uint32_t kphase = (STAGES == 1) ? 1 : 0, vphase = 0;
 
-      for (int j = 0; j < ntiles; ++j) {
-        const bool more = (j + 1 < ntiles);
-  #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1, 0x83);
-          if (t == 0) mbar_wait(&v_full[vstage], vphase, 0x84);
-          if (more && t == 0) mbar_wait(&k_full[kstage], kphase, 0x85);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t vbase = sV + vstage * CF::kKVBytes;
-  #pragma unroll
-            for (int k = 0; k < BN / 16; ++k) {
-              // A = P_t in TMEM: 16 keys = 8 packed 32-bit columns per K step
-              umma_f16_ts(o_col[t], s_col[t] + k * 8, make_desc_sw128(vbase + k * 2048, BN * 128, 1024),
-                          idesc_pv, (j | k) != 0);
-            }
-            if (t == 1) umma_commit(&v_empty[vstage]);
-            if (!more) umma_commit(&o_done[t]);
-            if (more) {
-              issue_qk(t, kstage);
-              umma_commit(&s_full[t]);
-              if (t == 1) umma_commit(&k_empty[kstage]);
-            }
+    for (int j = 0; j < ntiles; ++j) {
+      const bool more = (j + 1 < ntiles);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], j & 1, 0x83);
+        if (t == 0) mbar_wait(&v_full[vstage], vphase, 0x84);
+        if (more && t == 0) mbar_wait(&k_full[kstage], kphase, 0x85);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t vbase = sV + vstage * CF::kKVBytes;
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) {
+            // A = P_t in TMEM: 16 keys = 8 packed 32-bit columns per K step
+            umma_f16_ts(o_col[t], s_col[t] + k * 8, make_desc_sw128(vbase + k * 2048, BN * 128, 1024),
+                        idesc_pv, (j | k) != 0);
           }
-          __syncwarp();
+          if (t == 1) umma_commit(&v_empty[vstage]);
+          if (!more) umma_commit(&o_done[t]);
+          if (more) {
+            issue_qk(t, kstage);
+            umma_commit(&s_full[t]);
+            if (t == 1) umma_commit(&k_empty[kstage]);
+          }
         }
-        if (++vstage == STAGES) { vstage = 0; vphase ^= 1; }
-        if (more) {
-          if (++kstage == STAGES) { kstage = 0; kphase ^= 1; }
-        }
+        __syncwarp();
+      }
+      if (++vstage == STAGES) { vstage = 0; vphase ^= 1; }
+      if (more) {
+        if (++kstage == STAGES) { kstage = 0; kphase ^= 1; }
       }
     }
   }
@@ -412,7 +352,6 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
   d.O = q->O;
   d.ldo = q->ldo;
   d.scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  d.dyn = option(OPT_ATTN_DYN) != 0 ? 1 : 0;
   auto kern = attn2_tc_kernel<T, D, BN, POLY, MINB, NSTG>;
   static bool attr_set = false;
   if (!attr_set) {

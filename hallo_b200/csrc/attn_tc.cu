@@ -30,7 +30,6 @@ struct AttnDev {
   void* O;
   long long ldo;
   float scale_log2;   // d^-0.5 * log2(e)
-  int dyn;            // attn2: the MMA warp serves whichever query tile is ready first (option attn_dyn)
 };
 
 template <int D, int BN, int STAGES>
