@@ -64,7 +64,9 @@ __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { 
 
 constexpr int kPanelCols = 32;                        // output columns per staged panel (TMA-store epilogue)
 constexpr int kPanelBytes = kBM * kPanelCols * 2;     // 128 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B
-constexpr int kEpiBufs = 3;                           // panel buffers per warp group: store in flight | being written | residual landing
+constexpr int kEpiBufs = 4;                           // panel buffers per warp group: store in flight | being written | 2 residuals landing
+                                                      // (3 buffers = residual requested 2 panels ahead, less than one HBM latency at K = 320:
+                                                      //  profiles/r2_ncu_summaries.json gemm_k320)
 
 template <int BN, int STAGES, int CG, bool TEPI = false>
 struct GemmSmem {
@@ -842,7 +844,7 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
   if (tepi_env && aligned && p->scatter == nullptr) {
     const bool geglu = (p->flags & HB_EPI_GEGLU) != 0;
     if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
-    if (p->N % 192 == 0) return launch_gemm<T, 192, 6, 2, true>(p, s);
+    if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true>(p, s);
     if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
   }
   // option gemm_fill (opt-in, untested on hardware): when the widest N tile leaves SM pairs idle (small M: the
