@@ -328,6 +328,19 @@ class DenoiseEngine:
         halves, frames = list(sh.halves), list(sh.frames)
         f, fl, nb, nm, H = self.f, self.fl, self.nb, self.nm, cfg.heads
         win = self.window
+        trace = os.environ.get("HALLO_B200_TRACE_WINDOW")          # debugging aid: host wall time per section (synchronised)
+        if trace:
+            import time
+            torch.cuda.synchronize()
+            _t = [time.perf_counter()]
+
+            def mark(what):
+                torch.cuda.synchronize()
+                _t.append(time.perf_counter())
+                print(f"# begin_window {what}: {(_t[-1] - _t[-2]) * 1e3:.2f} ms", flush=True)
+        else:
+            def mark(what):
+                pass
         fr_idx = torch.tensor(frames, device=dev)
         # global (b f) row ids of the local rows, in local order
         rows = [b * f + g for b in halves for g in frames]
@@ -355,6 +368,7 @@ class DenoiseEngine:
             for lv, t in enumerate(m):
                 self._wset(f"mask.{nme}.{lv}", t.to(dev, dt)[rid].reshape(-1).contiguous())
         ms = [float(x) for x in motion_scale] if motion_scale is not None else [1.0, 1.0, 1.0]
+        mark("per-frame tensors (audio, mask_cond_fea, masks)")
 
         for b in W.blocks:
             lv = self._block_level(b.name)
@@ -403,6 +417,7 @@ class DenoiseEngine:
                         ops.groupnorm(win[f"{l.attn}.motion"], W[f"{tt}.norm.w"], W[f"{tt}.norm.b"], gn18, ws,
                                       n_frames=nb * nm, hw=L, groups=cfg.norm_num_groups, eps=1e-6,
                                       fpb_in=nm, fpb_out=nm + fl, frame_off=0)
+            mark(f"block {b.name}")
         if self.arena is not None:
             # ranks meet once per window on the device (flag barrier, stream-ordered, no host round trip): a peer's first
             # scatter store of the new window cannot overtake this rank's window set-up
