@@ -61,7 +61,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "attn_v1"     force the single-tile attention kernel                                              (default 0)
  *   "xattn_tc"    tcgen05 cross-attention (0: CUDA-core kernel)                                       (default 1)
  *   "tattn_mma"   temporal attention on warp-level tensor-core MMAs (0: CUDA cores)                   (default 1)
- *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1) */
+ *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1)
+ *   "attn_split"  head_dim 40: S / P handed over in two 32-key halves (next half's QK^T under this half's softmax) (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 
