@@ -13,7 +13,6 @@ static int dispatch_attn(const hb_attention_params* p, cudaStream_t s) {
     // v2 (two query tiles per CTA, P in TMEM) when a frame has at least one full pair of tiles; the
     // single-tile kernel otherwise (small L) and for head_dim 160 at small L.
     case 40:
-      if (p->L >= 256 && !v1 && option(OPT_ATTN_SPLIT) != 0) return launch_attn4<T>(p, s);   // half-split schedule (A/B)
       if (p->L >= 256 && !v1 && occ2 != 0) {
         if (poly == 4) return launch_attn2<T, 40, 64, 4, 2>(p, s);
         if (poly == 3) return launch_attn2<T, 40, 64, 3, 2>(p, s);

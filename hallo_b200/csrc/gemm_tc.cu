@@ -6,6 +6,13 @@
 //                 warp w drains TMEM lanes 32*(w%4).. and accumulator columns (w-2)/4 * BN/2 ..
 //
 // Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of tile i.
+//
+// Split-K (p.splits = S > 1, chosen by the host when the tiles cover less than half of the SMs): the grid holds one
+// CTA (pair) per (tile, split); split s runs k-blocks [s*kper, (s+1)*kper).  Splits 1.. store their raw fp32
+// accumulators to the workspace ([tile][split-1][pair rank][column][row]: coalesced along rows) and bump one counter
+// per (tile, rank, epilogue warp); split 0 waits for S-1 arrivals on the counter of each of its epilogue warps, adds
+// the partials in split order and runs the usual epilogue.  All CTAs of such a grid are co-resident (<= 1 per SM),
+// so the wait cannot deadlock; the summation order is fixed, so results do not depend on timing.
 // Tiles are walked n-fastest so the CTAs running concurrently share the same A rows in L2.
 //
 // Implicit conv: the A operand of tap (kh,kw) is the NHWC box shifted by (kh-1, kw-1); TMA's
@@ -55,9 +62,28 @@ struct GemmDev {
   float ln_eps;
   float* stats_out;
   hb_row_scatter sc;   // sc.seg > 0: output rows go to peer buffers (direct epilogue only)
+  int splits;          // split-K factor S (1 = off); S > 1 => gridDim.x == tiles * S * CG
+  float* ws;           // S > 1: fp32 partial tiles
+  int* cnt;            // S > 1: arrival counters, [tile][rank][epilogue warp], zero between launches
   // conv geometry
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
+
+// split-K: wait until `need` partial tiles have been published on *cnt, then re-arm the counter for the next launch
+__device__ __forceinline__ void splitk_wait(int* cnt, int need) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(cnt) : "memory");
+    if (v >= need) break;
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(&g_hb_error, 0x36u | (blockIdx.x << 8));
+      __trap();
+    }
+    __nanosleep(64);
+  }
+  *cnt = 0;
+}
 
 __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_x16(taddr, r); }
 __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_x32(taddr, r); }
@@ -149,13 +175,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
   const int kblocks = p.K / kBK;
   const int cin_blocks = CONV ? p.cin / kBK : 1;
+  // split-K: CTA (pair) c owns unit (tile c / S, split c % S) and nothing else -> every tile loop below runs once
+  const int S = p.splits;
+  const int split = S > 1 ? cta_first % S : 0;
+  const int first = S > 1 ? cta_first / S : cta_first;
+  const int stride = S > 1 ? num_tiles : cta_stride;
+  const int kper = (kblocks + S - 1) / S;
+  const int kb0 = split * kper;
+  const int kb1 = (kb0 + kper < kblocks) ? kb0 + kper : kblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cta_first; t < num_tiles; t += cta_stride) {
+      for (int t = first; t < num_tiles; t += stride) {
         const int tm = (t / p.tiles_n) * CG + (int)rank;
         const int tn = t % p.tiles_n;
         int n0 = 0, h0 = 0, w0 = 0;
@@ -169,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           h0 = hb_ * p.box_h;
           w0 = wb * p.box_w;
         }
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x11);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           uint8_t* sb = sa + SM::kABytes;
@@ -218,13 +252,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int it = 0;
     if (leader)   // in a pair only the leader CTA issues MMAs (for both SMs)
-    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
+    for (int t = first; t < num_tiles; t += stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1, 0x21);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 0x22);
         tc_fence_after();
         if (lane == 0) {
@@ -235,15 +269,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 32 B (16 halfs) along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            if (CG == 2) umma_f16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) umma_f16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           if (CG == 2) {
             umma_commit_cg2_mc(&empty_bar[stage]);
-            if (kb == kblocks - 1) umma_commit_cg2_mc(&tfull_bar[as]);
+            if (kb == kb1 - 1) umma_commit_cg2_mc(&tfull_bar[as]);
           } else {
             umma_commit(&empty_bar[stage]);
-            if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
           }
         }
         __syncwarp();
@@ -253,6 +287,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (split != 0) {
+    // ===================== split-K partial: raw fp32 accumulators -> workspace =====================
+    // each warp stores exactly the (rows, columns) that the same warp of the reducing CTA reads back
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    constexpr int UW = TEPI ? 32 : (((BN / 2) % 32 == 0) ? 32 : 16);
+    const int panels = (geglu ? BN / 64 : BN / 32);
+    const int my_panels = (panels - grp + 1) / 2;
+    const int nunits = TEPI ? (geglu ? 2 * my_panels : my_panels) : BN / 2 / UW;
+    const int t = first;
+    mbar_wait(&tfull_bar[0], 0, 0x35);
+    tc_fence_after();
+    float* ws = p.ws + ((((size_t)t * (S - 1) + (split - 1)) * CG + rank) * BN) * kBM + quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int u = 0; u < nunits; ++u) {
+      const int col = TEPI ? (geglu ? (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 : (grp + 2 * u) * 32) : grp * (BN / 2) + u * UW;
+      uint32_t r[UW];
+      tmem_ld_cw(taddr + col, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < UW; ++j) __stcg(ws + (size_t)(col + j) * kBM, __uint_as_float(r[j]));
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(p.cnt + ((t * CG + (int)rank) * 8 + (warp - 2)), 1);
   } else if (TEPI) {
     // ===================== epilogue warps, shared-memory staged + TMA stores =====================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
@@ -292,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     // residual prefetch iterator (elected thread only): the next (tile, panel) of this group to request
-    int pf_t = cta_first, pf_i = 0, pf_b = 0;
+    int pf_t = first, pf_i = 0, pf_b = 0;
     auto prefetch_residual = [&]() {
       if (pf_t >= num_tiles) return;
       int tm, tn, n0, h0, w0;
@@ -304,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++pf_b == kEpiBufs) pf_b = 0;
       if (++pf_i == my_panels) {
         pf_i = 0;
-        pf_t += cta_stride;
+        pf_t += stride;
       }
     };
     // panel q of this group lives in buffer q % kEpiBufs.  At the end of panel q the elected thread issues
@@ -318,7 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int b = 0;                            // buffer of the current panel
     uint32_t bphase = 0;                  // parity of res_full[b] for the current round through the buffers
     int it = 0;
-    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
+    for (int t = first; t < num_tiles; t += stride, ++it) {
       int tm, tn, n0, h0, w0;
       tile_origin(t, tm, tn, n0, h0, w0);
       const int as = it & 1;
@@ -352,6 +412,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
+      const float* wsr = nullptr;          // split-K: partial tiles of splits 1.. for this lane's row
+      if (S > 1) {
+        if (lane == 0) splitk_wait(p.cnt + ((t * CG + (int)rank) * 8 + (warp - 2)), S - 1);
+        __threadfence();
+        __syncwarp();
+        wsr = p.ws + (((size_t)t * (S - 1)) * CG + rank) * BN * kBM + r_in_tile;
+      }
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
       // accumulator column of unit u: plain -> panel (grp + 2u); GEGLU -> panel (grp + 2(u/2)), half (u & 1)
       auto unit_col = [&](int u) { return geglu ? (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 : (grp + 2 * u) * 32; };
@@ -373,6 +440,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (S > 1) {
+          for (int s2 = 0; s2 < S - 1; ++s2) {
+            const float* w = wsr + ((size_t)s2 * CG * BN + unit_col(u)) * kBM;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldcg(w + j * kBM);
+          }
+        }
         if (p.ln_stats != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -501,7 +575,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
     const int chalf = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int it = 0;
-    for (int t = cta_first; t < num_tiles; t += cta_stride, ++it) {
+    for (int t = first; t < num_tiles; t += stride, ++it) {
       const int tm = (t / p.tiles_n) * CG + (int)rank;
       const int tn = t % p.tiles_n;
       const int as = it & 1;
@@ -552,6 +626,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
+      const float* wsr = nullptr;          // split-K: partial tiles of splits 1.. for this lane's row
+      if (S > 1) {
+        if (lane == 0) splitk_wait(p.cnt + ((t * CG + (int)rank) * 8 + (warp - 2)), S - 1);
+        __threadfence();
+        __syncwarp();
+        wsr = p.ws + (((size_t)t * (S - 1)) * CG + rank) * BN * kBM + r_in_tile;
+      }
       // this warp owns TMEM lanes [32*quarter, +32) and accumulator columns [chalf*BN/2, +BN/2), CW at a time
       // (CW = 32 when the half-tile allows it: more independent work per TMEM load for the GELU epilogue)
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
@@ -569,6 +650,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[CW];
 #pragma unroll
           for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+          if (S > 1) {
+            for (int s2 = 0; s2 < S - 1; ++s2) {
+              const float* w = wsr + ((size_t)s2 * CG * BN + chalf * (BN / 2) + c * CW) * kBM;
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] += __ldcg(w + j * kBM);
+            }
+          }
           if (p.ln_stats != nullptr) {
 #pragma unroll
             for (int j = 0; j < CW; j += 4) {
@@ -686,6 +774,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CG == 2) tmem_dealloc_cg2<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
+
+constexpr long long kSplitKCounterBytes = 8192;     // head of the split-K workspace: arrival counters
+static int g_last_splits = 1;                       // split factor of the most recent launch (tests / diagnostics)
 
 // pick the NHWC box (box_w, box_h, box_n), box_w*box_h*box_n == 128, that covers the image batch with the
 // fewest tiles; boxes may overhang (TMA zero-fills, the epilogue masks), so any image size works.
@@ -807,7 +898,27 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   const int tiles = ((d.tiles_m + CG - 1) / CG) * d.tiles_n;      // (pairs of) tiles
   if (tiles <= 0) return HB_OK;
   const int max_ctas = num_sms() / CG;
-  const int grid = (tiles < max_ctas ? tiles : max_ctas) * CG;
+  // split-K: a CTA streams kblocks/S operand stages (32 KB each) and the reducing CTA reads S-1 partial tiles
+  // (128 x BN fp32) back, so the per-CTA traffic is smallest near S = sqrt(kblocks / 4); below 16 k-blocks it never pays
+  d.splits = 1;
+  const int kblocks = q->K / kBK;
+  if (option(OPT_GEMM_SPLITK) != 0 && q->workspace != nullptr && tiles * 2 <= max_ctas && kblocks >= 16 &&
+      (long long)tiles * CG * 8 * (long long)sizeof(int) <= kSplitKCounterBytes) {
+    int S = (int)(sqrtf((float)kblocks / 4.0f) + 0.5f);
+    if (S > max_ctas / tiles) S = max_ctas / tiles;
+    if (S > 16) S = 16;
+    const long long tile_bytes = (long long)CG * BN * kBM * (long long)sizeof(float);
+    const long long room = (q->workspace_bytes - kSplitKCounterBytes) / tile_bytes;      // partial tiles that fit
+    while (S > 1 && (long long)tiles * (S - 1) > room) --S;
+    while (S > 1 && (S - 1) * ((kblocks + S - 1) / S) >= kblocks) --S;                  // no empty split
+    if (S > 1) {
+      d.splits = S;
+      d.cnt = reinterpret_cast<int*>(q->workspace);
+      d.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->workspace) + kSplitKCounterBytes);
+    }
+  }
+  g_last_splits = d.splits;
+  const int grid = (d.splits > 1 ? tiles * d.splits : (tiles < max_ctas ? tiles : max_ctas)) * CG;
   auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true, CG, TEPI>
                          : gemm_tc_kernel<T, BN, STAGES, false, CG, TEPI>;
   static bool attr_set[2] = {false, false};
@@ -868,6 +979,13 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
 
 }  // namespace hb
 
+extern "C" long long hallo_b200_gemm_workspace_bytes(void) {
+  // counters + one 128 x 256 fp32 partial tile for every CTA of a 160-SM grid
+  return hb::kSplitKCounterBytes + 160LL * 256 * hb::kBM * (long long)sizeof(float);
+}
+
+extern "C" int hallo_b200_gemm_last_splits(void) { return hb::g_last_splits; }
+
 extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
   using namespace hb;
   if (p == nullptr || p->A == nullptr || p->W == nullptr || p->C == nullptr)
@@ -886,6 +1004,8 @@ extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
                                (p->M + p->scatter->seg - 1) / p->scatter->seg > (long long)HB_MAX_PEERS * p->scatter->segs_per_dest))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: row scatter needs a plain GEMM without residual and <= %d destinations",
                 HB_MAX_PEERS);
+  if (p->workspace != nullptr && ((reinterpret_cast<uintptr_t>(p->workspace) & 15) != 0 || p->workspace_bytes < 0))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: workspace must be 16-byte aligned");
   if (p->A2 != nullptr && (p->K1 % kBK != 0 || p->K1 <= 0 || p->K1 >= p->K || p->conv3x3))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: bad K split %d of %d", p->K1, p->K);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

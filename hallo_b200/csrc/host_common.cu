@@ -10,7 +10,7 @@ namespace hb {
 char g_last_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
 
-static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_occ2", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "attn_split"};
+static const char* const kOptionNames[OPT_COUNT] = {"gemm_tepi", "gemm_1cta", "attn_occ2", "attn_poly", "attn_v1", "xattn_tc", "tattn_mma", "gemm_fill", "gn_fused", "gemm_splitk"};
 // defaults: the kernels promoted after their round-2 hardware runs (profiles/r2_first_call_*) are ON; setting an
 // option to 0 selects the previous-generation kernel (A/B measurements, shapes the new kernel does not cover)
 static const int kOptionDefaults[OPT_COUNT] = {1, 0, 1, 0, 0, 1, 1, 1, 1, 0};
@@ -103,7 +103,7 @@ int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const
 
 extern "C" {
 
-int hallo_b200_abi_version(void) { return 2; }
+int hallo_b200_abi_version(void) { return 3; }
 int hallo_b200_sizeof_gemm_params(void) { return (int)sizeof(hb_gemm_params); }
 int hallo_b200_sizeof_attention_params(void) { return (int)sizeof(hb_attention_params); }
 

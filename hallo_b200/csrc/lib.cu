@@ -4,7 +4,6 @@
 #include "gemm_tc.cu"
 #include "attn_tc.cu"
 #include "attn2_tc.cu"
-#include "attn4_tc.cu"
 #include "attn_api.cu"
 #include "xattn_tc.cu"
 #include "tattn_mma.cu"

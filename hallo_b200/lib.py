@@ -37,6 +37,7 @@ class GemmParams(C.Structure):
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p),
         ("scatter", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -81,6 +82,7 @@ def load() -> C.CDLL:
     lib.hallo_b200_device_error.argtypes = [C.POINTER(C.c_uint)]
     lib.hallo_b200_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.hallo_b200_get_option.argtypes = [C.c_char_p]
+    lib.hallo_b200_gemm_workspace_bytes.restype = C.c_int64
     _lib = lib
     return lib
 

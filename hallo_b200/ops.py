@@ -6,6 +6,7 @@ captured into a CUDA graph) and writes into caller-provided output tensors.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional
 
 import torch
@@ -61,6 +62,29 @@ def _rowmajor_ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
+_tls = threading.local()
+
+
+def gemm_workspace_bytes() -> int:
+    return int(lib.load().hallo_b200_gemm_workspace_bytes())
+
+
+def _bind_workspace(p, device) -> None:
+    """Split-K scratch (hb_gemm_params.workspace): one zero-filled buffer per (host thread, device), allocated at the
+    first eager GEMM.  Every GEMM a thread launches goes to that thread's current stream, so no two GEMMs that may run
+    concurrently share it (thread-rank tests: one buffer per rank thread).  Never allocated inside a graph capture: a
+    GEMM captured before any eager one simply runs unsplit."""
+    pool = getattr(_tls, "gemm_ws", None)
+    if pool is None:
+        pool = _tls.gemm_ws = {}
+    ws = pool.get(device.index)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return
+        ws = pool[device.index] = torch.zeros(gemm_workspace_bytes(), dtype=torch.uint8, device=device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+
+
 @_timed(lambda a, w, out, **kw: f"gemm M{a.shape[0]} N{w.shape[0]} K{w.shape[1]}" + (" geglu" if kw.get("geglu") else ""))
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
@@ -102,6 +126,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     if scatter is not None:
         assert residual is None
         p.scatter = C.addressof(scatter)
+    _bind_workspace(p, a.device)
     lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "gemm")
     return out
 
@@ -139,6 +164,7 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor, *, bias:
     p.alpha = 1.0
     p.conv3x3 = 1
     p.img_n, p.img_h, p.img_w = n, h, w_
+    _bind_workspace(p, x.device)
     lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "conv3x3")
     return out
 
@@ -314,6 +340,7 @@ def conv3x3_stride2(x_planes: torch.Tensor, w_packed: torch.Tensor, out: torch.T
     p.alpha = 1.0
     p.conv3x3 = 2
     p.img_n, p.img_h, p.img_w = n, ho, wo
+    _bind_workspace(p, x_planes.device)
     lib.check(lib.load().hallo_b200_gemm(C.byref(p), lib.current_stream()), "conv3x3_stride2")
     return out
 

@@ -62,7 +62,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "xattn_tc"    tcgen05 cross-attention (0: CUDA-core kernel)                                       (default 1)
  *   "tattn_mma"   temporal attention on warp-level tensor-core MMAs (0: CUDA cores)                   (default 1)
  *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1)
- *   "attn_split"  head_dim 40: S / P handed over in two 32-key halves (next half's QK^T under this half's softmax) (default 0) */
+ *   "gemm_splitk" split the K loop of a GEMM / conv whose tiles fill less than half of the SMs over several CTAs
+ *                 (fp32 partials in the caller's workspace, fixed summation order)                       (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 
@@ -136,6 +137,13 @@ typedef struct {
   /* Output-row scatter (multi-GPU, see "Peer memory" below): NULL = rows go to C + row*ldc.  Direct-store epilogue
    * only; residual must be NULL. */
   const struct hb_row_scatter* scatter;
+  /* Split-K scratch (option "gemm_splitk"): device memory owned by the caller, zero-filled once, never shared by two
+   * GEMMs that may run concurrently (one per engine / stream).  When the tiles of a launch cover less than half of
+   * the SMs and K >= 1024, the K loop is divided over several CTAs per tile; CTAs 1.. write fp32 partial tiles here
+   * and CTA 0 adds them in split order (deterministic) before its epilogue.  hallo_b200_gemm_workspace_bytes() is
+   * the size that never limits the split; a smaller buffer lowers the split count, NULL / 0 turns it off. */
+  void* workspace;
+  long long workspace_bytes;
 } hb_gemm_params;
 
 /* Output row r of the GEMM is split as s = r / seg, q = r % seg, d = s / segs_per_dest, i = s % segs_per_dest and
@@ -152,6 +160,9 @@ typedef struct hb_row_scatter {
 } hb_row_scatter;
 
 int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream);
+long long hallo_b200_gemm_workspace_bytes(void);
+/* split factor the most recent hallo_b200_gemm call of this process used (1 = unsplit): tests / diagnostics */
+int hallo_b200_gemm_last_splits(void);
 
 /* ------------------------------------------------------------------------------------------
  * hallo_b200_attention -- fused softmax(Q K^T / sqrt(d)) V, tcgen05 + TMEM, flash-style.

@@ -133,3 +133,106 @@ def test_layernorm_folded_into_gemm(M, C, N, geglu):
     ops.gemm(x, wg, out, bias=bb, geglu=geglu, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-5)
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 3e-3
+
+
+def _with_splitk(fn):
+    """fn() with option gemm_splitk on, then off; returns (split result, split factor used, unsplit result)."""
+    from hallo_b200 import lib
+    lib.set_option("gemm_splitk", 1)
+    try:
+        a = fn().clone()
+        torch.cuda.synchronize()
+        splits = int(lib.load().hallo_b200_gemm_last_splits())
+        b = fn().clone()                                   # second launch: counters must have been re-armed
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("gemm_splitk", 0)
+    c = fn().clone()
+    torch.cuda.synchronize()
+    assert int(lib.load().hallo_b200_gemm_last_splits()) == 1
+    assert torch.equal(a, b), "split-K summation order must not depend on timing"
+    return a, splits, c
+
+
+@pytest.mark.parametrize("tepi", [1, 0])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,geglu", [(256, 1280, 1280, False), (256, 1280, 5120, False), (1024, 1280, 5120, False),
+                                         (200, 960, 2560, False), (256, 320, 1024, False), (8, 1280, 1280, False),
+                                         (64, 640, 2048, False), (256, 5120, 1280, True), (512, 2560, 1024, True)])
+def test_gemm_split_k_option(M, N, K, geglu, dtype, tepi):
+    """Option gemm_splitk (include/hallo_b200.h): K loop of a few-tile GEMM divided over several CTAs, fp32 partials
+    reduced by split 0 in fixed order -- every kernel template, both epilogues, full epilogue (bias, residual, row scale)."""
+    from hallo_b200 import lib, ops
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev, dtype)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, dtype)
+    b = torch.randn(N, generator=g).to(dev, dtype)
+    n_out = N // 2 if geglu else N
+    res = torch.randn(M, n_out, generator=g).to(dev, dtype)
+    rs = torch.rand(M, generator=g).to(dev, dtype)
+    if geglu:
+        w, b = ops.pack_geglu_weight(w, b)
+    out = torch.empty(M, n_out, device=dev, dtype=dtype)
+    lib.set_option("gemm_tepi", tepi)
+    try:
+        got, splits, unsplit = _with_splitk(lambda: ops.gemm(a, w, out, bias=b, residual=res, row_scale=rs, geglu=geglu))
+    finally:
+        lib.set_option("gemm_tepi", 1)
+    if tepi or M <= 256:           # (the direct epilogue picks narrow tiles for small M: the larger cases already fill the SMs)
+        assert splits > 1, "shape chosen to split"
+    h = a.float() @ (w.float().t())
+    h = h + b.float()
+    if geglu:
+        h = h[:, 0::2] * F.gelu(h[:, 1::2])
+    ref = h * rs.float()[:, None] + res.float()
+    print(f"M{M} N{N} K{K} geglu={geglu} tepi={tepi}: S={splits}, rel L2 vs fp32 {rel_l2(got, ref):.2e}, vs unsplit {rel_l2(got, unsplit):.2e}")
+    assert rel_l2(got, ref) < TOL[dtype]
+    assert rel_l2(got, unsplit) < TOL[dtype]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 8, 8, 1280, 1280), (4, 16, 16, 1280, 640), (4, 8, 8, 2560, 1280),
+                                            (2, 16, 16, 640, 320), (4, 4, 4, 1280, 1280)])
+def test_conv3x3_split_k_option(n, h, w, cin, cout):
+    from hallo_b200 import ops
+    dev = _dev()
+    dtype = torch.float16
+    g = torch.Generator(device="cpu").manual_seed(n + h + cin)
+    x = torch.randn(n, cin, h, w, generator=g).to(dev, dtype)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(dev, dtype)
+    b = torch.randn(cout, generator=g).to(dev, dtype)
+    res = torch.randn(n * h * w, cout, generator=g).to(dev, dtype)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv3x3_weight(wt)
+    out = torch.empty(n * h * w, cout, device=dev, dtype=dtype)
+    got, splits, unsplit = _with_splitk(lambda: ops.conv3x3(x_nhwc, wp, out, bias=b, residual=res))
+    assert splits > 1
+    ref = F.conv2d(x.float(), wt.float(), b.float(), padding=1).permute(0, 2, 3, 1).reshape(n * h * w, cout) + res.float()
+    print(f"conv n{n} {h}x{w} {cin}->{cout}: S={splits}, rel L2 vs fp32 {rel_l2(got, ref):.2e}")
+    assert rel_l2(got, ref) < 2e-3
+    assert rel_l2(got, unsplit) < 2e-3
+
+
+def test_split_k_interleaved_shapes_reuse_the_workspace():
+    """Back-to-back split GEMMs of different shapes share one workspace and one set of counters: each launch must
+    leave the counters at zero for the next (stream order), whatever its tile count."""
+    from hallo_b200 import lib, ops
+    dev = _dev()
+    dtype = torch.float16
+    g = torch.Generator(device="cpu").manual_seed(99)
+    shapes = [(256, 1280, 5120), (1024, 1280, 1280), (128, 640, 2560), (256, 1280, 5120), (512, 960, 1920)]
+    cases = []
+    for M, N, K in shapes:
+        a = torch.randn(M, K, generator=g).to(dev, dtype)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, dtype)
+        cases.append((a, w, torch.empty(M, N, device=dev, dtype=dtype)))
+    lib.set_option("gemm_splitk", 1)
+    try:
+        for _ in range(5):
+            for a, w, out in cases:
+                ops.gemm(a, w, out)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("gemm_splitk", 0)
+    for a, w, out in cases:
+        assert rel_l2(out, a.float() @ w.float().t()) < 2e-3
