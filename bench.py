@@ -241,6 +241,42 @@ def run_clip(args, rank, world, dev, dt, config):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def kineto_report(eng, path, replays=3):
+    """Warm, in-graph kernel durations (CUPTI activity records of `replays` graph replays): per kernel name x grid the
+    count / mean / total per step, plus how much of the step no kernel was running (launch gaps + dependency stalls)."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(replays):
+            eng.step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()
+           and e.time_range is not None]
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs if "memcpy" not in e.name.lower()
+                 and "memset" not in e.name.lower()), key=lambda t: t[0])
+    if not ks:
+        open(path, "w").write("no kernel records (CUPTI unavailable?)\n")
+        return
+    span = ks[-1][1] - ks[0][0]
+    busy, gaps, cur_end = 0.0, [], ks[0][0]
+    agg = {}
+    for a, b, name in ks:
+        if a > cur_end:
+            gaps.append(a - cur_end)
+        busy += max(0.0, b - max(a, cur_end))
+        cur_end = max(cur_end, b)
+        short = name.split("(")[0].replace("void hb::", "")[:70]
+        c = agg.setdefault(short, [0, 0.0])
+        c[0] += 1
+        c[1] += b - a
+    with open(path, "w") as f:
+        f.write(f"{replays} graph replays: span {span / replays / 1e3:.3f} ms/step, kernels busy {busy / replays / 1e3:.3f} ms/step, "
+                f"idle {(span - busy) / replays / 1e3:.3f} ms/step in {len(gaps) // replays} gaps "
+                f"(median gap {sorted(gaps)[len(gaps) // 2]:.2f} us), {len(ks) // replays} kernels/step\n")
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"  {t / replays / 1e3:8.3f} ms/step  x{n // replays:4d}  {t / n:8.2f} us each  {name}\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +295,9 @@ def main():
                     help="wrap ONE eager denoising step in cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`: "
                          "the launch list then holds exactly the step's kernels, not the set-up's)")
     ap.add_argument("--profile-ops", action="store_true", help="print a per-op time table of one eager forward")
+    ap.add_argument("--kineto", default="", metavar="FILE",
+                    help="after the timed run, trace 3 graph replays with torch.profiler (CUPTI) and write the per-kernel "
+                         "in-graph durations and the idle gaps between kernels to FILE (diagnostic, not a bench value)")
     ap.add_argument("--emulate-shard", type=int, default=0, metavar="R",
                     help="single GPU: run the workload of ONE rank of an R-rank job (cond half, first frame group, no "
                          "collectives) -- for ncu / op profiles of the sharded shapes; the JSON line is marked invalid")
@@ -454,6 +493,9 @@ def main():
     e2e_fps = args.frames / (N_DDIM * e2e_ms * 1e-3)
     h2d = lat_host.numel() * 4 + window_bytes() // N_DDIM
     d2h = lat_back.numel() * 4
+
+    if args.kineto and rank == 0:
+        kineto_report(eng, args.kineto)
 
     # ---------------- optional per-op table: one eager step on EVERY rank (the collectives need all of them) ----------------
     prof_saved = None
