@@ -242,39 +242,58 @@ def run_clip(args, rank, world, dev, dt, config):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def kineto_report(eng, path, replays=3):
-    """Warm, in-graph kernel durations (CUPTI activity records of `replays` graph replays): per kernel name x grid the
-    count / mean / total per step, plus how much of the step no kernel was running (launch gaps + dependency stalls)."""
+    """Warm, in-graph kernel durations (CUPTI activity records of `replays` graph replays): per kernel name the
+    count / mean / total per step, how much of the step no kernel was running (launch gaps + dependency stalls), and
+    -- in `path`.seq -- the kernels of one replay in launch order with their grids, next to the op sequence of one
+    eager step (`path`.ops: one line per hallo_b200.ops call, same order) so that durations can be matched to shapes."""
+    import tempfile
     from torch.profiler import ProfilerActivity, profile
+    from hallo_b200 import ops
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(replays):
             eng.step()
         torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()
-           and e.time_range is not None]
-    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs if "memcpy" not in e.name.lower()
-                 and "memset" not in e.name.lower()), key=lambda t: t[0])
+    tmp = tempfile.mktemp(suffix=".json")
+    prof.export_chrome_trace(tmp)
+    trace = json.load(open(tmp))
+    os.remove(tmp)
+    ks = sorted(((e["ts"], e["ts"] + e["dur"], e["name"], e.get("args", {}).get("grid"))
+                 for e in trace.get("traceEvents", []) if e.get("cat") == "kernel"), key=lambda t: t[0])
     if not ks:
         open(path, "w").write("no kernel records (CUPTI unavailable?)\n")
         return
     span = ks[-1][1] - ks[0][0]
     busy, gaps, cur_end = 0.0, [], ks[0][0]
     agg = {}
-    for a, b, name in ks:
+    shorten = lambda name: name.split("(")[0].replace("void hb::", "")[:70]
+    for a, b, name, _ in ks:
         if a > cur_end:
             gaps.append(a - cur_end)
         busy += max(0.0, b - max(a, cur_end))
         cur_end = max(cur_end, b)
-        short = name.split("(")[0].replace("void hb::", "")[:70]
-        c = agg.setdefault(short, [0, 0.0])
+        c = agg.setdefault(shorten(name), [0, 0.0])
         c[0] += 1
         c[1] += b - a
     with open(path, "w") as f:
         f.write(f"{replays} graph replays: span {span / replays / 1e3:.3f} ms/step, kernels busy {busy / replays / 1e3:.3f} ms/step, "
                 f"idle {(span - busy) / replays / 1e3:.3f} ms/step in {len(gaps) // replays} gaps "
-                f"(median gap {sorted(gaps)[len(gaps) // 2]:.2f} us), {len(ks) // replays} kernels/step\n")
+                f"(median gap {sorted(gaps)[len(gaps) // 2] if gaps else 0:.2f} us), {len(ks) // replays} kernels/step\n")
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"  {t / replays / 1e3:8.3f} ms/step  x{n // replays:4d}  {t / n:8.2f} us each  {name}\n")
+    per = len(ks) // replays
+    with open(path + ".seq", "w") as f:
+        for a, b, name, grid in ks[per:2 * per]:
+            f.write(f"{b - a:9.2f} us  grid {grid}  {shorten(name)}\n")
+    # the same step, eager, to list the ops in launch order (their event timings are not used)
+    ops.PROFILE = []
+    g, eng.graph = eng.graph, None
+    eng.step()
+    torch.cuda.synchronize()
+    names = [name for name, _, _ in ops.PROFILE]
+    ops.PROFILE = None
+    eng.graph = g
+    open(path + ".ops", "w").write("\n".join(names) + "\n")
 
 
 def main():

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2,
 attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                 const __grid_constant__ CUtensorMap tmV1, const AttnDev p) {
+  pdl_wait();
   using CF = Attn2Cfg<D, BN, NSTG>;
   constexpr int STAGES = CF::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -106,6 +107,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == kAllocWarp) tmem_alloc<CF::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  pdl_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -359,7 +361,7 @@ static int launch_attn2(const hb_attention_params* q, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((q->L + 255) / 256, q->heads, q->frames);
-  kern<<<grid, MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2, CF::kTotal, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, d);
+  launch_kernel(kern, grid, MINB == 1 ? kAttn2Threads : kAttn2ThreadsOcc2, CF::kTotal, stream, tmQ, tmK0, tmV0, tmK1, tmV1, d);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

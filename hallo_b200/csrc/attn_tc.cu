@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                const __grid_constant__ CUtensorMap tmV1, const AttnDev p) {
+  pdl_wait();
   using CF = AttnCfg<D, BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -101,6 +102,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 2) tmem_alloc<CF::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  pdl_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -369,7 +371,7 @@ static int launch_attn(const hb_attention_params* q, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((q->L + 127) / 128, q->heads, q->frames);
-  kern<<<grid, kAttnThreads, CF::kTotal, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, d);
+  launch_kernel(kern, grid, kAttnThreads, CF::kTotal, stream, tmQ, tmK0, tmV0, tmK1, tmV1, d);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
                                                         float eps, const float* __restrict__ pe,
                                                         const int* __restrict__ pe_index, int L,
                                                         int frames) {
+  pdl_wait();
+  pdl_launch();
   // LPR lanes cooperate on one row (C = LPR * VPL * 8 channels); a warp handles 32 / LPR rows.
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x1,
                                                        const T* __restrict__ x2, int C2, int HW,
                                                        int pix_per_cta, int G,
                                                        float* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];   // [PY][C] sums, then [PY][C] sumsq
   const int C = C1 + C2;
   const int nvec = C >> 3;
@@ -177,6 +181,8 @@ template <typename T>
 __global__ void gn_finalize_kernel(const float* __restrict__ stats, int nchunks, const T* __restrict__ gamma,
                                    const T* __restrict__ beta, float eps, int C, int G, int HW,
                                    float* __restrict__ scsh) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float gsum[64][2];
   const int n = blockIdx.x;
   const int cpg = C / G;
@@ -222,6 +228,8 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const T* __restrict__ x1,
                                                         int HW, int G, const T* __restrict__ gamma,
                                                         const T* __restrict__ beta, float eps, int silu,
                                                         T* __restrict__ out, int fpb_in, int fpb_out, int frame_off) {
+  pdl_wait();
+  pdl_launch();
   using Vec = typename GnVec<V>::type;
   extern __shared__ uint4 gn_slab_raw[];           // [HW][cpg / (2V)] vectors of V channel pairs
   Vec* slab = reinterpret_cast<Vec*>(gn_slab_raw);
@@ -325,6 +333,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x1,
                                                        int pix_per_cta, const float* __restrict__ scsh,
                                                        int silu, T* __restrict__ out, int fpb_in,
                                                        int fpb_out, int frame_off, const GnScatter scat) {
+  pdl_wait();
+  pdl_launch();
   // thread (cv, py): fixed 8 channels, strided pixels -> per-channel scale/shift live in registers
   const int C = C1 + C2;
   const int nvec = C >> 3;
@@ -379,6 +389,8 @@ __global__ void __launch_bounds__(128) xattn_kernel(
     const T* __restrict__ Q, long long ldq, int q_region_stride, const T* __restrict__ K,
     const T* __restrict__ V, long long ldkv, int kv_region_stride, T* __restrict__ O, long long ldo,
     int o_region_stride, int L, int heads, int d, int kv_frame_div, float scale_log2) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float smf[];   // K [NK][d] then V [NK][d] as float
   const int frame = blockIdx.y;
   const int head = blockIdx.z % heads;
@@ -451,6 +463,8 @@ __global__ void __launch_bounds__(288) tattn_kernel(const T* __restrict__ Q, lon
                                                     T* __restrict__ O, long long ldo, int batch,
                                                     int Fq, int Fk, int L, int heads, int d,
                                                     float scale_log2) {
+  pdl_wait();
+  pdl_launch();
   // thread order (head, query frame, pixel, batch): the Fq query frames of a pixel sit next to each other,
   // so the 2*Fk K/V rows of that pixel are fetched from L2 once and re-read by the other frames through L1.
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -523,6 +537,8 @@ __global__ void __launch_bounds__(576) tattn_smem_kernel(const T* __restrict__ Q
                                                          T* __restrict__ O, long long ldo, int Fq, int Fk,
                                                          int L, int heads, int d, int pix_per_cta,
                                                          float scale_log2) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ uint4 sm4[];
   const int C = heads * d;
   const int cvec = C >> 3;                       // 16-byte vectors per row
@@ -605,6 +621,8 @@ __global__ void __launch_bounds__(576) tattn_smem_kernel(const T* __restrict__ Q
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W,
                                   int C) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const long long total = (long long)N * (2 * H) * (2 * W) * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -625,6 +643,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ out, 
 template <typename T>
 __global__ void phase_split_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W,
                                    int C) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int H2 = H >> 1, W2 = W >> 1;
   const long long total = (long long)N * H * W * nvec;
@@ -648,6 +668,8 @@ __global__ void phase_split_kernel(const T* __restrict__ x, T* __restrict__ out,
 template <typename T>
 __global__ void im2col_latent_kernel(const float* __restrict__ lat, T* __restrict__ out, int batch,
                                      int Cl, int F, int H, int W, long long batch_stride) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)batch * F * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -682,6 +704,8 @@ __global__ void im2col_latent_kernel(const float* __restrict__ lat, T* __restric
 template <typename T>
 __global__ void timestep_embed_kernel(const float* __restrict__ t_table, const int* __restrict__ step,
                                       T* __restrict__ out, int rows, int dim) {
+  pdl_wait();
+  pdl_launch();
   const int half = dim >> 1;
   const float t = t_table[*step];
   for (int i = threadIdx.x; i < rows * dim; i += blockDim.x) {
@@ -702,6 +726,8 @@ __global__ void cfg_ddim_kernel(const T* __restrict__ model_out, long long ldm,
                                 float* __restrict__ lat, const float* __restrict__ coef,
                                 const int* __restrict__ step, float guidance, int Cl, int F, int HW,
                                 float* __restrict__ v_out) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)F * HW;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -723,6 +749,8 @@ __global__ void cfg_ddim_kernel(const T* __restrict__ model_out, long long ldm,
 }
 
 __global__ void advance_step_kernel(int* step, int n_steps) {
+  pdl_wait();
+  pdl_launch();
   if (threadIdx.x == 0 && blockIdx.x == 0) *step = (*step + 1) % n_steps;
 }
 
@@ -730,6 +758,8 @@ __global__ void advance_step_kernel(int* step, int n_steps) {
 template <typename T>
 __global__ void nhwc_to_bcfhw_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
                                      int B, int C, int F, int HW) {
+  pdl_wait();
+  pdl_launch();
   const long long total = (long long)B * F * HW;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -743,6 +773,8 @@ __global__ void nhwc_to_bcfhw_kernel(const T* __restrict__ x, long long ld, floa
 
 template <typename T>
 __global__ void add_rows_kernel(T* __restrict__ x, const T* __restrict__ y, long long nvec) {
+  pdl_wait();
+  pdl_launch();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
@@ -787,7 +819,7 @@ extern "C" int hallo_b200_layernorm(int dtype, const void* x, int64_t ldx, void*
   {                                                                                                     \
     const int rpb = wpb * (32 / LPR);                                                                   \
     const int grid = (rows + rpb - 1) / rpb;                                                            \
-    layernorm_kernel<T, LPR, VPL><<<grid, wpb * 32, 0, s>>>((const T*)x, ldx, (T*)out, ldo,             \
+    launch_kernel(layernorm_kernel<T, LPR, VPL>, grid, wpb * 32, 0, s, (const T*)x, ldx, (T*)out, ldo,             \
                                                              (const T*)gamma, (const T*)beta, rows, C,  \
                                                              eps, pe, pe_index, L > 0 ? L : 1,          \
                                                              frames > 0 ? frames : 1);                  \
@@ -858,7 +890,7 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
       HB_DISPATCH_T(dtype, {
         auto kern = vw == 4 ? gn_fused_kernel<T, 4> : (vw == 2 ? gn_fused_kernel<T, 2> : gn_fused_kernel<T, 1>);
         HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        kern<<<dim3(G, N), 256, slab, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, G, (const T*)gamma, (const T*)beta,
+        launch_kernel(kern, dim3(G, N), 256, slab, s, (const T*)x1, C1, (const T*)x2, C2, HW, G, (const T*)gamma, (const T*)beta,
                                            eps, silu, (T*)out, fpb_in, fpb_out, frame_off);
       })
       HB_LAUNCH_CHECK();
@@ -878,15 +910,15 @@ static int groupnorm_impl(int dtype, const void* x1, int C1, const void* x2, int
   const size_t smem = sizeof(float) * 2 * PY * C;
   if (fpb_in <= 0) { fpb_in = N; fpb_out = N; frame_off = 0; }
   HB_DISPATCH_T(dtype, {
-    gn_stats_kernel<T><<<g1, threads, smem, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, pix_per_cta, G,
+    launch_kernel(gn_stats_kernel<T>, g1, threads, smem, s, (const T*)x1, C1, (const T*)x2, C2, HW, pix_per_cta, G,
                                                  stats_ws);
     HB_LAUNCH_CHECK();
-    gn_finalize_kernel<T><<<N, 256, 0, s>>>(stats_ws, (int)g1.x, (const T*)gamma, (const T*)beta, eps, C, G, HW, scsh);
+    launch_kernel(gn_finalize_kernel<T>, N, 256, 0, s, stats_ws, (int)g1.x, (const T*)gamma, (const T*)beta, eps, C, G, HW, scsh);
     HB_LAUNCH_CHECK();
     int ppc = 64;                                     // pixels per CTA of the apply pass
     if (HW < ppc) ppc = HW;
     dim3 g2((HW + ppc - 1) / ppc, N);
-    gn_apply_kernel<T><<<g2, threads, 0, s>>>((const T*)x1, C1, (const T*)x2, C2, HW, ppc, scsh, silu, (T*)out,
+    launch_kernel(gn_apply_kernel<T>, g2, threads, 0, s, (const T*)x1, C1, (const T*)x2, C2, HW, ppc, scsh, silu, (T*)out,
                                               fpb_in, fpb_out, frame_off, sc);
   })
   HB_LAUNCH_CHECK();
@@ -915,11 +947,11 @@ extern "C" int hallo_b200_cross_attention(int dtype, const void* Q, int64_t ldq,
   const size_t smem = sizeof(float) * 2 * n_keys * head_dim;
   HB_DISPATCH_T(dtype, {
     if (n_keys == 4)
-      xattn_kernel<T, 4><<<grid, 128, smem, s>>>((const T*)Q, ldq, q_region_stride, (const T*)K,
+      launch_kernel(xattn_kernel<T, 4>, grid, 128, smem, s, (const T*)Q, ldq, q_region_stride, (const T*)K,
                                                  (const T*)V, ldkv, kv_region_stride, (T*)O, ldo,
                                                  o_region_stride, L, heads, head_dim, kv_frame_div, sc);
     else
-      xattn_kernel<T, 32><<<grid, 128, smem, s>>>((const T*)Q, ldq, q_region_stride, (const T*)K,
+      launch_kernel(xattn_kernel<T, 32>, grid, 128, smem, s, (const T*)Q, ldq, q_region_stride, (const T*)K,
                                                   (const T*)V, ldkv, kv_region_stride, (T*)O, ldo,
                                                   o_region_stride, L, heads, head_dim, kv_frame_div, sc);
   })
@@ -954,7 +986,7 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
       HB_DISPATCH_T(dtype, {
         auto kern = Fk <= 18 ? tattn_smem_kernel<T, 18> : tattn_smem_kernel<T, 32>;
         HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grid2, ppc * per_pix, smem, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O, ldo, Fq,
+        launch_kernel(kern, grid2, ppc * per_pix, smem, s, (const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O, ldo, Fq,
                                                Fk, L, heads, head_dim, ppc, sc2);
       })
       HB_LAUNCH_CHECK();
@@ -967,10 +999,10 @@ extern "C" int hallo_b200_temporal_attention(int dtype, const void* Q, int64_t l
   const float sc = (float)(1.4426950408889634 / sqrt((double)head_dim));
   HB_DISPATCH_T(dtype, {
     if (Fk <= 18)
-      tattn_kernel<T, 18><<<grid, block, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
+      launch_kernel(tattn_kernel<T, 18>, grid, block, 0, s, (const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
                                                ldo, batch, Fq, Fk, L, heads, head_dim, sc);
     else
-      tattn_kernel<T, 32><<<grid, block, 0, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
+      launch_kernel(tattn_kernel<T, 32>, grid, block, 0, s, (const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O,
                                                ldo, batch, Fq, Fk, L, heads, head_dim, sc);
   })
   HB_LAUNCH_CHECK();
@@ -984,7 +1016,7 @@ extern "C" int hallo_b200_upsample2x(int dtype, const void* x, void* out, int N,
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)N * 4 * H * W * (C / 8);
   HB_DISPATCH_T(dtype, {
-    upsample2x_kernel<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)x, (T*)out, N, H, W, C);
+    launch_kernel(upsample2x_kernel<T>, grid_for(total, 256), 256, 0, s, (const T*)x, (T*)out, N, H, W, C);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;
@@ -997,7 +1029,7 @@ extern "C" int hallo_b200_phase_split(int dtype, const void* x, void* out, int N
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)N * H * W * (C / 8);
   HB_DISPATCH_T(dtype, {
-    phase_split_kernel<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)x, (T*)out, N, H, W, C);
+    launch_kernel(phase_split_kernel<T>, grid_for(total, 256), 256, 0, s, (const T*)x, (T*)out, N, H, W, C);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;
@@ -1010,7 +1042,7 @@ extern "C" int hallo_b200_im2col_latent(int dtype, const float* latents, void* o
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)batch * F * H * W;
   HB_DISPATCH_T(dtype, {
-    im2col_latent_kernel<T><<<(int)((total + 127) / 128), 128, 0, s>>>(
+    launch_kernel(im2col_latent_kernel<T>, (int)((total + 127) / 128), 128, 0, s, 
         latents, (T*)out, batch, Cl, F, H, W, per_half_latents ? (long long)Cl * F * H * W : 0LL);
   })
   HB_LAUNCH_CHECK();
@@ -1021,7 +1053,7 @@ extern "C" int hallo_b200_timestep_embed(int dtype, const float* t_table, const 
                                          int rows, int dim, hb_stream_t stream) {
   if (!t_table || !step || !out) return fail(HB_ERR_NULL, "timestep_embed: null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  HB_DISPATCH_T(dtype, { timestep_embed_kernel<T><<<1, 256, 0, s>>>(t_table, step, (T*)out, rows, dim); })
+  HB_DISPATCH_T(dtype, { launch_kernel(timestep_embed_kernel<T>, 1, 256, 0, s, t_table, step, (T*)out, rows, dim); })
   HB_LAUNCH_CHECK();
   return HB_OK;
 }
@@ -1033,7 +1065,7 @@ extern "C" int hallo_b200_cfg_ddim_step(int dtype, const void* model_out, int64_
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)F * HW;
   HB_DISPATCH_T(dtype, {
-    cfg_ddim_kernel<T><<<(int)((total + 127) / 128), 128, 0, s>>>((const T*)model_out, ldm, latents, coef,
+    launch_kernel(cfg_ddim_kernel<T>, (int)((total + 127) / 128), 128, 0, s, (const T*)model_out, ldm, latents, coef,
                                                                   step, guidance, Cl, F, HW, v_out);
   })
   HB_LAUNCH_CHECK();
@@ -1042,7 +1074,7 @@ extern "C" int hallo_b200_cfg_ddim_step(int dtype, const void* model_out, int64_
 
 extern "C" int hallo_b200_advance_step(int32_t* step, int n_steps, hb_stream_t stream) {
   if (!step) return fail(HB_ERR_NULL, "advance_step: null pointer");
-  advance_step_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step, n_steps);
+  launch_kernel(advance_step_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream), step, n_steps);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }
@@ -1053,7 +1085,7 @@ extern "C" int hallo_b200_tokens_to_bcfhw(int dtype, const void* x, int64_t ld, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = (long long)B * F * HW;
   HB_DISPATCH_T(dtype, {
-    nhwc_to_bcfhw_kernel<T><<<(int)((total + 127) / 128), 128, 0, s>>>((const T*)x, ld, out, B, C, F, HW);
+    launch_kernel(nhwc_to_bcfhw_kernel<T>, (int)((total + 127) / 128), 128, 0, s, (const T*)x, ld, out, B, C, F, HW);
   })
   HB_LAUNCH_CHECK();
   return HB_OK;

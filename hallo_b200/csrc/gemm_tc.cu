@@ -170,6 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all();        // peer barriers must be initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above (barriers, TMEM, tensor-map prefetch) may overlap the predecessor's tail
+  pdl_launch();
 
   // a pair walks (pairs of) M tiles: tile t covers M tiles {CG*tm2, CG*tm2 + 1}; this CTA takes tm = CG*tm2 + rank
   const int num_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
@@ -409,6 +411,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
       float osum = 0.f, osq = 0.f;
+      // accumulator column of unit u: plain -> panel (grp + 2u); GEGLU -> panel (grp + 2(u/2)), half (u & 1)
+      auto unit_col = [&](int u) { return geglu ? (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 : (grp + 2 * u) * 32; };
+      // the per-column epilogue vectors of this warp's units do not depend on the accumulator: pull them into L1 while
+      // the MMAs run (lane u takes unit u; a unit is 64 B of bias / one 128 B line of column sums)
+      if (lane < my_units) {
+        const int pc = tn * BN + unit_col(lane);
+        if (bias != nullptr) prefetch_l1(bias + pc);
+        if (gb_row != nullptr) prefetch_l1(gb_row + pc);
+        if (p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
+      }
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
@@ -420,8 +432,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wsr = p.ws + (((size_t)t * (S - 1)) * CG + rank) * BN * kBM + r_in_tile;
       }
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
-      // accumulator column of unit u: plain -> panel (grp + 2u); GEGLU -> panel (grp + 2(u/2)), half (u & 1)
-      auto unit_col = [&](int u) { return geglu ? (grp + 2 * (u >> 1)) * 64 + (u & 1) * 32 : (grp + 2 * u) * 32; };
       uint32_t racc[2][32];
       tmem_ld_x32(taddr + unit_col(0), racc[0]);
 #pragma unroll
@@ -563,7 +573,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(&tempty_bar[as]);
       }
     }
-    if (elected) bulk_wait_group<0>();      // global writes of the last panels performed before the CTA retires
+    // the staging buffers must outlive the READS of the last stores; their global writes complete with the grid
+    if (elected) bulk_wait_group_read<0>();
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -622,6 +633,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long dd = sg / p.sc.segs_per_dest;
         const long long ii = sg - dd * p.sc.segs_per_dest;
         crow = reinterpret_cast<T*>(p.sc.base[dd]) + (ii * p.sc.seg_stride + p.sc.row0 + qq) * p.ldc;
+      }
+      // epilogue vectors of this warp's BN/2 columns -> L1 while the MMAs run (one lane per 64 B)
+      {
+        const int pc = tn * BN + chalf * (BN / 2) + lane * 32;
+        if (lane * 32 < BN / 2 && pc < p.N) {
+          if (bias != nullptr) prefetch_l1(bias + pc);
+          if (gb_row != nullptr) prefetch_l1(gb_row + pc);
+          if (p.ln_colsum != nullptr) {
+            prefetch_l1(p.ln_colsum + pc);
+            if (pc + 16 < p.N) prefetch_l1(p.ln_colsum + pc + 16);
+          }
+        }
       }
 
       mbar_wait(&tfull_bar[as], aphase, 0x31);
@@ -926,19 +949,7 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set[q->conv3x3 ? 1 : 0] = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = SM::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  HB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, d, tmC, tmR));
+  HB_CUDA_CHECK(launch_kernel_cluster(kern, dim3(grid), dim3(kGemmThreads), SM::kTotal, stream, CG, tmA, tmA2, tmB, d, tmC, tmR));
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

@@ -16,7 +16,7 @@ extern char g_last_error[512];
 extern std::atomic<int64_t> g_launch_count;
 
 // run-time kernel-selection switches (hallo_b200_set_option); initial value from HALLO_B200_<NAME>
-enum Option { OPT_GEMM_TEPI = 0, OPT_GEMM_1CTA, OPT_ATTN_OCC2, OPT_ATTN_POLY, OPT_ATTN_V1, OPT_XATTN_TC, OPT_TATTN_MMA, OPT_GEMM_FILL, OPT_GN_FUSED, OPT_GEMM_SPLITK, OPT_COUNT };
+enum Option { OPT_GEMM_TEPI = 0, OPT_GEMM_1CTA, OPT_ATTN_OCC2, OPT_ATTN_POLY, OPT_ATTN_V1, OPT_XATTN_TC, OPT_TATTN_MMA, OPT_GEMM_FILL, OPT_GN_FUSED, OPT_GEMM_SPLITK, OPT_PDL, OPT_COUNT };
 int option(Option o);
 
 inline int fail(int code, const char* fmt, ...) {
@@ -65,6 +65,41 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// Every kernel launch of the library goes through here.  `cluster` > 1 sets the cluster dimension; with option "pdl"
+// the launch carries programmatic stream serialization, i.e. the kernel may become resident while its predecessor
+// drains -- every kernel launched this way calls pdl_wait() (ptx.cuh) before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (option(OPT_PDL) != 0) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  return launch_kernel_cluster(kern, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 }  // namespace hb

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags pf, in
 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long nvec) {
+  pdl_wait();
+  pdl_launch();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 ua = reinterpret_cast<const uint4*>(a)[i];
     const uint4 ub = reinterpret_cast<const uint4*>(b)[i];
@@ -129,9 +131,9 @@ extern "C" int hallo_b200_add(int dtype, const void* a, const void* b, void* out
   long long g = (nvec + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(g < cap ? (g > 0 ? g : 1) : cap);
-  if (dtype == HB_F16) add_kernel<__half><<<grid, 256, 0, s>>>((const __half*)a, (const __half*)b, (__half*)out, nvec);
+  if (dtype == HB_F16) launch_kernel(add_kernel<__half>, grid, 256, 0, s, (const __half*)a, (const __half*)b, (__half*)out, nvec);
   else if (dtype == HB_BF16)
-    add_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, nvec);
+    launch_kernel(add_kernel<__nv_bfloat16>, grid, 256, 0, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, nvec);
   else return fail(HB_ERR_BAD_DTYPE, "add: dtype %d", dtype);
   HB_LAUNCH_CHECK();
   return HB_OK;

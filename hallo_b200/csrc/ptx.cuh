@@ -78,6 +78,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 // ------------------------------------------------------------------------------------------
 // TMA tiled loads (tensor maps are passed as __grid_constant__ kernel parameters)
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (option "pdl"): a kernel launched with programmatic stream serialization may start
+// while its predecessor in the stream is still draining.  pdl_wait() blocks until the predecessor grid has completed
+// and its memory is visible (a no-op without the launch attribute) and must precede every global access; pdl_launch()
+// lets the successor's CTAs be scheduled -- issued only after this CTA holds all the TMEM it will ever allocate, so
+// an early successor can never sit on TMEM columns that a not-yet-resident CTA of this grid is waiting for.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }

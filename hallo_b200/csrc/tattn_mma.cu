@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(kTattnThreads)
 tattn_mma_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__ K, const T* __restrict__ V,
                  long long ldkv, T* __restrict__ O, long long ldo, int Fq, int Fk, int L, int heads, int pix_per_cta,
                  int ps, int fs, float scale_log2) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ uint4 tattn_smem[];
   constexpr int KS = (D + 15) / 16;           // k-steps of Q K^T
   constexpr bool kHalfStep = (D % 16) == 8;   // the last k-step only holds 8 real dims
@@ -216,7 +218,7 @@ static int launch_tattn_mma(const void* Q, long long ldq, const void* K, const v
   }
   dim3 grid((L + pix - 1) / pix, batch);
   const float sc = (float)(1.4426950408889634 / sqrt((double)D));
-  kern<<<grid, kTattnThreads, smem, s>>>((const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O, ldo, Fq, Fk, L, heads,
+  launch_kernel(kern, grid, kTattnThreads, smem, s, (const T*)Q, ldq, (const T*)K, (const T*)V, ldkv, (T*)O, ldo, Fq, Fk, L, heads,
                                          pix, ps, fs, sc);
   HB_LAUNCH_CHECK();
   return HB_OK;

@@ -48,6 +48,7 @@ template <typename T, int D, int NK>
 __global__ void __launch_bounds__(kXThreads, 1)
 xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const XAttnDev p) {
+  pdl_wait();
   using CF = XCfg<D, NK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -93,6 +94,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_alloc<CF::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  pdl_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -288,7 +290,7 @@ static int launch_xattn(int dtype, const void* Q, long long ldq, const void* K, 
     attr_set = true;
   }
   dim3 grid(slabs, frames, heads * regions);
-  kern<<<grid, kXThreads, CF::kTotal, stream>>>(tmQ, tmK, tmV, d);
+  launch_kernel(kern, grid, kXThreads, CF::kTotal, stream, tmQ, tmK, tmV, d);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

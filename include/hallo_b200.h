@@ -63,7 +63,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "tattn_mma"   temporal attention on warp-level tensor-core MMAs (0: CUDA cores)                   (default 1)
  *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1)
  *   "gemm_splitk" split the K loop of a GEMM / conv whose tiles fill less than half of the SMs over several CTAs
- *                 (fp32 partials in the caller's workspace, fixed summation order)                       (default 1) */
+ *                 (fp32 partials in the caller's workspace, fixed summation order)                       (default 1)
+ *   "pdl"         programmatic dependent launch: a kernel's prologue overlaps the tail of its predecessor     (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
 

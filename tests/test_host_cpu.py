@@ -57,7 +57,7 @@ def test_kernel_selection_options_roundtrip():
     g.build()
     from hallo_b200 import lib
     defaults = {"gemm_tepi": 1, "gemm_1cta": 0, "gemm_fill": 1, "attn_occ2": 1, "attn_poly": 0, "attn_v1": 0,
-                "xattn_tc": 1, "tattn_mma": 1, "gn_fused": 1, "gemm_splitk": 1}
+                "xattn_tc": 1, "tattn_mma": 1, "gn_fused": 1, "gemm_splitk": 1, "pdl": 0}
     for name, dflt in defaults.items():
         if os.environ.get("HALLO_B200_" + name.upper()) is None:
             assert lib.get_option(name) == dflt, name

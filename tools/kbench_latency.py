@@ -49,7 +49,7 @@ def main():
     shapes = [(256, 1280, 1280), (1024, 1280, 1280), (4096, 640, 640), (16384, 320, 320), (1024, 640, 640), (256, 320, 320),
               (8192, 1280, 1280), (32768, 640, 640)]
     variants = [("default (pair, TMA-store epilogue)", {}), ("gemm_tepi=0 (pair, direct epilogue)", {"gemm_tepi": 0}),
-                ("gemm_1cta=1 (single CTA, direct)", {"gemm_1cta": 1}), ("gemm_tepi=0 gemm_fill=1", {"gemm_tepi": 0, "gemm_fill": 1})]
+                ("pdl=1 (prologue under the predecessor's tail)", {"pdl": 1}), ("gemm_splitk=0", {"gemm_splitk": 0})]
     for (M, N, K) in shapes:
         a = torch.randn(M, K, device=dev, dtype=torch.float16)
         w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.02
