@@ -799,6 +799,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 constexpr long long kSplitKCounterBytes = 8192;     // head of the split-K workspace: arrival counters
+constexpr int kSplitKMinBlocks = 32;                // shortest K loop (64-wide k-blocks) that is split
 static int g_last_splits = 1;                       // split factor of the most recent launch (tests / diagnostics)
 
 // pick the NHWC box (box_w, box_h, box_n), box_w*box_h*box_n == 128, that covers the image batch with the
@@ -922,10 +923,14 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   if (tiles <= 0) return HB_OK;
   const int max_ctas = num_sms() / CG;
   // split-K: a CTA streams kblocks/S operand stages (32 KB each) and the reducing CTA reads S-1 partial tiles
-  // (128 x BN fp32) back, so the per-CTA traffic is smallest near S = sqrt(kblocks / 4); below 16 k-blocks it never pays
+  // (128 x BN fp32) back, so the per-CTA traffic is smallest near S = sqrt(kblocks / 4).  The hand-over (partial
+  // store, fence, counter, read-back) costs ~4 us, which a K loop below kSplitKMinBlocks k-blocks does not win back
+  // (profiles/r2_kbench_latency_splitk.log); an option value > 1 overrides that threshold (A/B runs).
   d.splits = 1;
   const int kblocks = q->K / kBK;
-  if (option(OPT_GEMM_SPLITK) != 0 && q->workspace != nullptr && tiles * 2 <= max_ctas && kblocks >= 16 &&
+  const int splitk_opt = option(OPT_GEMM_SPLITK);
+  const int min_blocks = splitk_opt > 1 ? splitk_opt : kSplitKMinBlocks;
+  if (splitk_opt != 0 && q->workspace != nullptr && tiles * 2 <= max_ctas && kblocks >= min_blocks &&
       (long long)tiles * CG * 8 * (long long)sizeof(int) <= kSplitKCounterBytes) {
     int S = (int)(sqrtf((float)kblocks / 4.0f) + 0.5f);
     if (S > max_ctas / tiles) S = max_ctas / tiles;

@@ -63,7 +63,8 @@ int64_t hallo_b200_launch_count(int reset);
  *   "tattn_mma"   temporal attention on warp-level tensor-core MMAs (0: CUDA cores)                   (default 1)
  *   "gn_fused"    one-launch GroupNorm when a (frame, group) slab fits shared memory                  (default 1)
  *   "gemm_splitk" split the K loop of a GEMM / conv whose tiles fill less than half of the SMs over several CTAs
- *                 (fp32 partials in the caller's workspace, fixed summation order)                       (default 1)
+ *                 (fp32 partials in the caller's workspace, fixed summation order); 1 = for K >= 2048, a value
+ *                 n > 1 = for K >= 64 n                                                                  (default 1)
  *   "pdl"         programmatic dependent launch: a kernel's prologue overlaps the tail of its predecessor     (default 0) */
 int hallo_b200_set_option(const char* name, int value);
 int hallo_b200_get_option(const char* name);
@@ -140,7 +141,7 @@ typedef struct {
   const struct hb_row_scatter* scatter;
   /* Split-K scratch (option "gemm_splitk"): device memory owned by the caller, zero-filled once, never shared by two
    * GEMMs that may run concurrently (one per engine / stream).  When the tiles of a launch cover less than half of
-   * the SMs and K >= 1024, the K loop is divided over several CTAs per tile; CTAs 1.. write fp32 partial tiles here
+   * the SMs and K >= 2048, the K loop is divided over several CTAs per tile; CTAs 1.. write fp32 partial tiles here
    * and CTA 0 adds them in split order (deterministic) before its epilogue.  hallo_b200_gemm_workspace_bytes() is
    * the size that never limits the split; a smaller buffer lowers the split count, NULL / 0 turns it off. */
   void* workspace;

@@ -139,7 +139,7 @@ def _with_splitk(fn):
     """fn() with option gemm_splitk on, then off; returns (split result, split factor used, unsplit result)."""
     from hallo_b200 import lib
     was = int(lib.load().hallo_b200_get_option(b"gemm_splitk"))
-    lib.set_option("gemm_splitk", 1)
+    lib.set_option("gemm_splitk", 16)                      # > 1: split from 16 k-blocks on (the default needs 32)
     try:
         a = fn().clone()
         torch.cuda.synchronize()
@@ -229,7 +229,7 @@ def test_split_k_interleaved_shapes_reuse_the_workspace():
         w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, dtype)
         cases.append((a, w, torch.empty(M, N, device=dev, dtype=dtype)))
     was = int(lib.load().hallo_b200_get_option(b"gemm_splitk"))
-    lib.set_option("gemm_splitk", 1)
+    lib.set_option("gemm_splitk", 16)
     try:
         for _ in range(5):
             for a, w, out in cases:
