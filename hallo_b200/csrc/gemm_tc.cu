@@ -69,6 +69,34 @@ struct GemmDev {
   int cin, img_n, img_h, img_w, box_w, box_h, box_n, tiles_w, tiles_h, stride2;
 };
 
+// Timeline tracing (tools/gemm_trace.py builds a second library with -DHB_GEMM_TRACE): four recording threads per CTA
+// (TMA producer, MMA issuer, the elected thread of each epilogue group) append (event, index, clock64) records to a
+// global buffer set with hallo_b200_gemm_trace_buffer().  Compiles to nothing in the product library.
+#ifdef HB_GEMM_TRACE
+__device__ long long* g_gemm_trace = nullptr;
+constexpr int kTraceSlots = 256;                    // records per recorder
+struct Tracer {
+  long long* base;
+  int n;
+  __device__ Tracer(int recorder) {
+    base = g_gemm_trace ? g_gemm_trace + ((size_t)blockIdx.x * 4 + recorder) * (2 * kTraceSlots) : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void rec(int ev, int idx) {
+    if (base != nullptr && n < kTraceSlots) {
+      base[2 * n] = ((long long)ev << 32) | (unsigned)idx;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+#define HB_TRACE_DECL(name, recorder) Tracer name(recorder)
+#define HB_TRACE(name, ev, idx) name.rec(ev, idx)
+#else
+#define HB_TRACE_DECL(name, recorder)
+#define HB_TRACE(name, ev, idx)
+#endif
+
 // split-K: wait until `need` partial tiles have been published on *cnt, then re-arm the counter for the next launch
 __device__ __forceinline__ void splitk_wait(int* cnt, int need) {
   const long long t0 = clock64();
@@ -191,10 +219,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      HB_TRACE_DECL(tr, 0);
+      HB_TRACE(tr, 1, 0);
       for (int t = first; t < num_tiles; t += stride) {
         const int tm = (t / p.tiles_n) * CG + (int)rank;
         const int tn = t % p.tiles_n;
         int n0 = 0, h0 = 0, w0 = 0;
+        HB_TRACE(tr, 2, t);
         if (CONV) {
           int per_img = p.tiles_w * p.tiles_h;
           int nb = tm / per_img;
@@ -245,6 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1;
           }
         }
+        HB_TRACE(tr, 3, t);
       }
     }
   } else if (warp == 1) {
@@ -253,17 +285,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    HB_TRACE_DECL(tr, 1);
     if (leader)   // in a pair only the leader CTA issues MMAs (for both SMs)
     for (int t = first; t < num_tiles; t += stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if (lane == 0) HB_TRACE(tr, 10, t);
       mbar_wait(&tempty_bar[as], aphase ^ 1, 0x21);
       tc_fence_after();
+      if (lane == 0) HB_TRACE(tr, 11, t);
       const uint32_t d_tmem = tmem_base + as * kAccStride;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 0x22);
         tc_fence_after();
         if (lane == 0) {
+          if (kb == kb0) HB_TRACE(tr, 12, t);
+          if (kb == kb1 - 1) HB_TRACE(tr, 13, t);
           const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
           const uint32_t sb = sa + SM::kABytes;
           const uint64_t adesc = make_desc_sw128(sa, 16, 1024);
@@ -380,6 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int b = 0;                            // buffer of the current panel
     uint32_t bphase = 0;                  // parity of res_full[b] for the current round through the buffers
     int it = 0;
+    HB_TRACE_DECL(tr, 2 + grp);
     for (int t = first; t < num_tiles; t += stride, ++it) {
       int tm, tn, n0, h0, w0;
       tile_origin(t, tm, tn, n0, h0, w0);
@@ -422,8 +460,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
       }
 
+      if (elected) HB_TRACE(tr, 20, t);
       mbar_wait(&tfull_bar[as], aphase, 0x31);
       tc_fence_after();
+      if (elected) HB_TRACE(tr, 21, t);
       const float* wsr = nullptr;          // split-K: partial tiles of splits 1.. for this lane's row
       if (S > 1) {
         if (lane == 0) splitk_wait(p.cnt + ((t * CG + (int)rank) * 8 + (warp - 2)), S - 1);
@@ -445,7 +485,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool last_of_panel = !geglu || (u & 1) == 1;
         uint8_t* sbuf = stg + b * kPanelBytes;
         const uint32_t sbuf_u32 = smem_u32(sbuf);
-        if (first_of_panel && has_res) mbar_wait(&res_full[b], bphase, 0x33);
+        if (first_of_panel && has_res) {
+          if (elected) HB_TRACE(tr, 22, u);
+          mbar_wait(&res_full[b], bphase, 0x33);
+          if (elected) HB_TRACE(tr, 23, u);
+        }
 
         float v[32];
 #pragma unroll
@@ -545,14 +589,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (last_of_panel) {
+          if (elected) HB_TRACE(tr, 24, u);
           fence_proxy_async_smem();                       // generic-proxy writes -> visible to the TMA store
           named_bar_sync(1 + grp, 128);
           if (elected) {
+            HB_TRACE(tr, 25, u);
             const int ocol = tn * out_bn + (geglu ? (grp + 2 * (u >> 1)) : (grp + 2 * u)) * kPanelCols;
             if (CONV) tma_store_4d(&tmC, sbuf, ocol, w0, h0, n0);
             else tma_store_2d(&tmC, sbuf, ocol, tm * kBM);
             bulk_commit_group();
             bulk_wait_group_read<1>();                    // the previous panel's buffer is free again ...
+            HB_TRACE(tr, 26, u);
             if (has_res) prefetch_residual();             // ... and takes the residual of panel q + kEpiBufs - 1
           }
           __syncwarp();
@@ -1001,6 +1048,14 @@ extern "C" long long hallo_b200_gemm_workspace_bytes(void) {
 }
 
 extern "C" int hallo_b200_gemm_last_splits(void) { return hb::g_last_splits; }
+
+#ifdef HB_GEMM_TRACE
+// tools/gemm_trace.py only: buffer of gridDim.x * 4 recorders * 256 records * 2 int64 (NULL = off)
+extern "C" int hallo_b200_gemm_trace_buffer(void* buf) {
+  long long* p = reinterpret_cast<long long*>(buf);
+  return cudaMemcpyToSymbol(hb::g_gemm_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
   using namespace hb;
