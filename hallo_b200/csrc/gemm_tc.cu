@@ -491,10 +491,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elected) HB_TRACE(tr, 23, u);
         }
 
+        if (elected) HB_TRACE(tr, 27, u);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (S > 1) {
+#pragma unroll 1
           for (int s2 = 0; s2 < S - 1; ++s2) {
             const float* w = wsr + ((size_t)s2 * CG * BN + unit_col(u)) * kBM;
 #pragma unroll
@@ -529,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 8; ++k) v[j + k] += f[k];
           }
         }
+        if (elected) HB_TRACE(tr, 28, u);
         if (p.flags & HB_EPI_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -721,6 +724,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
           if (S > 1) {
+#pragma unroll 1
             for (int s2 = 0; s2 < S - 1; ++s2) {
               const float* w = wsr + ((size_t)s2 * CG * BN + chalf * (BN / 2) + c * CW) * kBM;
 #pragma unroll

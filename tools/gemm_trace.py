@@ -28,10 +28,11 @@ from hallo_b200 import lib, ops  # noqa: E402
 SLOTS = 256
 NAMES = {1: "start", 2: "prod.tile_begin", 3: "prod.tile_issued", 10: "mma.tile_begin", 11: "mma.acc_free", 12: "mma.first_stage",
          13: "mma.last_stage", 20: "epi.tile_begin", 21: "epi.acc_ready", 22: "epi.res_wait", 23: "epi.res_ready",
-         24: "epi.panel_written", 25: "epi.group_synced", 26: "epi.store_issued+prev_read"}
+         24: "epi.panel_written", 25: "epi.group_synced", 26: "epi.store_issued+prev_read", 27: "epi.unit_loaded",
+         28: "epi.unit_biased"}
 
 
-def run(M, N, K, geglu=False, residual=True, label=""):
+def run(M, N, K, geglu=False, residual=True, label="", use_bias=True, verbose=True):
     dev = "cuda"
     a = torch.randn(M, K, device=dev, dtype=torch.float16)
     w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.05
@@ -39,7 +40,7 @@ def run(M, N, K, geglu=False, residual=True, label=""):
     n_out = N // 2 if geglu else N
     out = torch.empty(M, n_out, device=dev, dtype=torch.float16)
     res = torch.randn(M, n_out, device=dev, dtype=torch.float16) if residual else None
-    fn = lambda: ops.gemm(a, w, out, bias=bias, residual=res, geglu=geglu)
+    fn = lambda: ops.gemm(a, w, out, bias=bias if use_bias else None, residual=res, geglu=geglu)
     h = lib.load()
     h.hallo_b200_gemm_trace_buffer.argtypes = [C.c_void_p]
     h.hallo_b200_gemm_trace_buffer(None)
@@ -58,7 +59,7 @@ def run(M, N, K, geglu=False, residual=True, label=""):
     torch.cuda.synchronize()
     h.hallo_b200_gemm_trace_buffer(None)
     rec = buf.cpu().view(148, 4, SLOTS, 2)
-    print(f"\n=== gemm M{M} N{N} K{K} geglu={geglu} residual={residual} {label}: {e0.elapsed_time(e1) * 1e3:.1f} us (cold L2)")
+    print(f"\n=== gemm M{M} N{N} K{K} geglu={geglu} residual={residual} bias={use_bias} {label}: {e0.elapsed_time(e1) * 1e3:.1f} us (cold L2)")
     import collections
     agg = collections.defaultdict(list)
     for cta in range(148):
@@ -69,7 +70,7 @@ def run(M, N, K, geglu=False, residual=True, label=""):
                 t0 = evs[0][2]
             for (e, i, t), (e2, i2, t2) in zip(evs, evs[1:]):
                 agg[(r, NAMES.get(e, e), NAMES.get(e2, e2))].append(t2 - t)
-            if cta in (0, 2) and evs and t0 is not None:
+            if verbose and cta in (0,) and evs and t0 is not None:
                 line = " ".join(f"{NAMES.get(e, e).split('.')[-1]}[{i}]@{t - t0}" for e, i, t in evs[:26])
                 print(f"  cta {cta} rec {r}: {line}")
     print("  mean clocks between consecutive events (count):")
@@ -79,7 +80,9 @@ def run(M, N, K, geglu=False, residual=True, label=""):
 
 if __name__ == "__main__":
     run(131072, 320, 320, label="L0 to_out / proj (x55 per step)")
-    run(131072, 960, 320, residual=False, label="L0 QKV")
-    run(131072, 2560, 320, geglu=True, residual=False, label="L0 GEGLU")
-    run(16384, 320, 320, label="L0 to_out, 1/8 shard")
-    run(32768, 640, 640, label="L1 to_out")
+    run(131072, 320, 320, residual=False, label="no residual", verbose=False)
+    run(131072, 320, 320, use_bias=False, label="no bias", verbose=False)
+    run(131072, 320, 320, residual=False, use_bias=False, label="plain", verbose=False)
+    run(131072, 960, 320, residual=False, use_bias=False, label="L0 QKV")
+    run(131072, 2560, 320, geglu=True, residual=False, label="L0 GEGLU", verbose=False)
+    run(32768, 640, 640, label="L1 to_out", verbose=False)
