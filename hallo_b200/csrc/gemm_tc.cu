@@ -141,7 +141,16 @@ struct GemmSmem {
 // 128 x 32 output panels into swizzled shared memory (conflict-free), an elected thread stores each panel with
 // one cp.async.bulk.tensor (clipped at the tensor edge, so no row masks) and the residual panel is prefetched
 // by TMA into the same buffer two panels ahead.
-template <typename T, int BN, int STAGES, bool CONV, int CG, bool TEPI = false>
+//
+// EPI (TEPI kernels only) fixes the epilogue at compile time: EPI_PLAIN = bias / group bias / row scale / residual,
+// EPI_GEGLU = the same with the (value, gate) GEGLU pairing, EPI_FULL = every option decided at run time (activation,
+// folded LayerNorm, row statistics).  One kernel with all options live is ~130 KB of SASS whose executed path hops over
+// the dead branches of four unrolled units: the epilogue warps then wait on instruction fetch ("no_inst" in
+// profiles/r2_ncu_gemm_k320_stalls.txt; 450 clk between two trace points with no work in between,
+// profiles/r2_gemm_trace_before.txt), and with K <= 640 the epilogue, not the MMA, sets the tile rate.
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_FULL = 2 };
+
+template <typename T, int BN, int STAGES, bool CONV, int CG, bool TEPI = false, int EPI = EPI_FULL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmDev p,
@@ -331,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // each warp stores exactly the (rows, columns) that the same warp of the reducing CTA reads back
     const int quarter = warp & 3;
     const int grp = (warp - 2) >> 2;
-    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    const bool geglu = (EPI == EPI_GEGLU) || (EPI == EPI_FULL && (p.flags & HB_EPI_GEGLU) != 0);
     constexpr int UW = TEPI ? 32 : (((BN / 2) % 32 == 0) ? 32 : 16);
     const int panels = (geglu ? BN / 64 : BN / 32);
     const int my_panels = (panels - grp + 1) / 2;
@@ -360,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* gbias = reinterpret_cast<const T*>(p.group_bias);
     const T* rscale = reinterpret_cast<const T*>(p.row_scale);
-    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    const bool geglu = (EPI == EPI_GEGLU) || (EPI == EPI_FULL && (p.flags & HB_EPI_GEGLU) != 0);
     const bool has_res = p.residual != nullptr;
     // a unit = 32 accumulator columns (one TMEM load); a panel = 32 output columns = 1 unit (2 with GEGLU)
     constexpr int kMaxUnits = (BN % 64 == 0) ? 2 * ((BN / 64 + 1) / 2) : (BN / 32 + 1) / 2;
@@ -442,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const T* gb_row = nullptr;
       if (gbias != nullptr && row_ok) gb_row = gbias + (row / p.rows_per_group) * p.ld_group_bias;
       float ln_mu = 0.f, ln_rstd = 1.f;
-      if (p.ln_stats != nullptr && row_ok) {
+      if (EPI == EPI_FULL && p.ln_stats != nullptr && row_ok) {
         const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * row);
         ln_mu = st.x / (float)p.K;
         const float var = fmaxf(st.y / (float)p.K - ln_mu * ln_mu, 0.f);
@@ -457,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int pc = tn * BN + unit_col(lane);
         if (bias != nullptr) prefetch_l1(bias + pc);
         if (gb_row != nullptr) prefetch_l1(gb_row + pc);
-        if (p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
+        if (EPI == EPI_FULL && p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
       }
 
       if (elected) HB_TRACE(tr, 20, t);
@@ -503,7 +512,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) v[j] += __ldcg(w + j * kBM);
           }
         }
-        if (p.ln_stats != nullptr) {
+        if (EPI == EPI_FULL && p.ln_stats != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + acol0 + j);
@@ -532,12 +541,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (elected) HB_TRACE(tr, 28, u);
-        if (p.flags & HB_EPI_SILU) {
+        if (EPI == EPI_FULL) {
+          if (p.flags & HB_EPI_SILU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-        } else if (p.flags & HB_EPI_RELU) {
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          } else if (p.flags & HB_EPI_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
         }
         if (geglu) {
           // (value, gate) pairs: 32 accumulator columns -> 16 outputs = chunks 2*(u&1), 2*(u&1)+1 of the panel row
@@ -581,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o4.z = Cvt<T>::pack2(w[4], w[5]);
             o4.w = Cvt<T>::pack2(w[6], w[7]);
             sts128(cell, o4);
-            if (p.stats_out != nullptr) {
+            if (EPI == EPI_FULL && p.stats_out != nullptr) {
               // statistics of the values as the next LayerNorm will read them (rounded to the storage type)
               const float2 q0 = Cvt<T>::unpack2(o4.x), q1 = Cvt<T>::unpack2(o4.y), q2 = Cvt<T>::unpack2(o4.z),
                            q3 = Cvt<T>::unpack2(o4.w);
@@ -612,7 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (p.stats_out != nullptr && row_ok) {
+      if (EPI == EPI_FULL && p.stats_out != nullptr && row_ok) {
         atomicAdd(p.stats_out + 2 * row, osum);
         atomicAdd(p.stats_out + 2 * row + 1, osq);
       }
@@ -871,7 +882,7 @@ static void pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
     }
 }
 
-template <typename T, int BN, int STAGES, int CG, bool TEPI = false>
+template <typename T, int BN, int STAGES, int CG, bool TEPI = false, int EPI = EPI_FULL>
 static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   using SM = GemmSmem<BN, STAGES, CG, TEPI>;
   static_assert(SM::kTotal <= 232448, "gemm smem budget");
@@ -998,8 +1009,15 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   }
   g_last_splits = d.splits;
   const int grid = (d.splits > 1 ? tiles * d.splits : (tiles < max_ctas ? tiles : max_ctas)) * CG;
-  auto kern = q->conv3x3 ? gemm_tc_kernel<T, BN, STAGES, true, CG, TEPI>
-                         : gemm_tc_kernel<T, BN, STAGES, false, CG, TEPI>;
+  // instantiated: the run-time-everything epilogue (EPI_FULL) for plain GEMMs and, without TEPI, convs; the
+  // specialised TEPI epilogues for plain GEMMs (PLAIN, GEGLU) and convs (PLAIN)
+  constexpr bool kConvOk = (EPI == EPI_PLAIN) || (EPI == EPI_FULL && !TEPI);
+  auto kern = gemm_tc_kernel<T, BN, STAGES, false, CG, TEPI, EPI>;
+  if constexpr (kConvOk) {
+    if (q->conv3x3) kern = gemm_tc_kernel<T, BN, STAGES, true, CG, TEPI, EPI>;
+  } else {
+    if (q->conv3x3) return fail(HB_ERR_BAD_SHAPE, "internal: conv3x3 routed to a GEMM-only epilogue");
+  }
   static bool attr_set[2] = {false, false};
   if (!attr_set[q->conv3x3 ? 1 : 0]) {
     HB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
@@ -1021,9 +1039,20 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(p->C) | reinterpret_cast<uintptr_t>(p->residual)) & 15) == 0;
   if (tepi_env && aligned && p->scatter == nullptr) {
     const bool geglu = (p->flags & HB_EPI_GEGLU) != 0;
-    if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
-    if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true>(p, s);
-    if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
+    // activation / folded LayerNorm / row statistics: the epilogue with every option live (plain GEMMs only)
+    const bool full = (p->flags & (HB_EPI_SILU | HB_EPI_RELU)) != 0 || p->ln_stats != nullptr || p->stats_out != nullptr;
+    if (!full && geglu) {
+      if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true, EPI_GEGLU>(p, s);
+      if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true, EPI_GEGLU>(p, s);
+    } else if (!full) {
+      if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true, EPI_PLAIN>(p, s);
+      if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true, EPI_PLAIN>(p, s);
+      if (p->N % 160 == 0) return launch_gemm<T, 160, 6, 2, true, EPI_PLAIN>(p, s);
+    } else if (!p->conv3x3) {
+      if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
+      if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true>(p, s);
+      if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
+    }
   }
   // option gemm_fill (opt-in, untested on hardware): when the widest N tile leaves SM pairs idle (small M: the
   // per-rank shapes of a sharded window, levels 2-3), trade shared-memory efficiency for occupancy with BN 128 / 64
