@@ -304,12 +304,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (lane == 0) HB_TRACE(tr, 11, t);
       const uint32_t d_tmem = tmem_base + as * kAccStride;
+#ifdef HB_GEMM_TRACE
+      long long wsum = 0;
+#endif
       for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef HB_GEMM_TRACE
+        const long long w0 = clock64();
+#endif
         mbar_wait(&full_bar[stage], phase, 0x22);
         tc_fence_after();
+#ifdef HB_GEMM_TRACE
+        wsum += clock64() - w0;
+#endif
         if (lane == 0) {
           if (kb == kb0) HB_TRACE(tr, 12, t);
-          if (kb == kb1 - 1) HB_TRACE(tr, 13, t);
+          if (kb == kb1 - 1) {
+            HB_TRACE(tr, 13, t);
+            HB_TRACE(tr, 14, (int)wsum);
+          }
           const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
           const uint32_t sb = sa + SM::kABytes;
           const uint64_t adesc = make_desc_sw128(sa, 16, 1024);
@@ -464,10 +476,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // the MMAs run (lane u takes unit u; a unit is 64 B of bias / one 128 B line of column sums)
       if (lane < my_units) {
         const int pc = tn * BN + unit_col(lane);
-        if (bias != nullptr) prefetch_l1(bias + pc);
         if (gb_row != nullptr) prefetch_l1(gb_row + pc);
         if (EPI == EPI_FULL && p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
       }
+      // the tile's bias, 8 columns per lane, requested now and consumed (by lane shuffles) after the accumulator wait
+      uint4 bias_v = make_uint4(0u, 0u, 0u, 0u);
+      if (bias != nullptr && lane * 8 < BN) bias_v = *reinterpret_cast<const uint4*>(bias + tn * BN + lane * 8);
 
       if (elected) HB_TRACE(tr, 20, t);
       mbar_wait(&tfull_bar[as], aphase, 0x31);
@@ -481,14 +495,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wsr = p.ws + (((size_t)t * (S - 1)) * CG + rank) * BN * kBM + r_in_tile;
       }
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
-      uint32_t racc[2][32];
-      tmem_ld_x32(taddr + unit_col(0), racc[0]);
-#pragma unroll
-      for (int u = 0; u < kMaxUnits; ++u) {
-        if (u >= my_units) break;
+      // ONE copy of the unit body (not unrolled: instruction-cache footprint, see the header of this kernel); the
+      // accumulator registers are copied out before the next unit's TMEM load is issued into them
+      uint32_t racc[32];
+      tmem_ld_x32(taddr + unit_col(0), racc);
+#pragma unroll 1
+      for (int u = 0; u < my_units; ++u) {
         tmem_ld_wait();
-        uint32_t(&r)[32] = racc[u & 1];
-        if (u + 1 < my_units) tmem_ld_x32(taddr + unit_col(u + 1), racc[(u + 1) & 1]);   // overlaps with the math below
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
+        if (u + 1 < my_units) tmem_ld_x32(taddr + unit_col(u + 1), racc);   // overlaps with the math below
         const int acol0 = tn * BN + unit_col(u);                   // first accumulator (= weight row) column
         const bool first_of_panel = !geglu || (u & 1) == 0;
         const bool last_of_panel = !geglu || (u & 1) == 1;
@@ -501,9 +518,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 
         if (elected) HB_TRACE(tr, 27, u);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (S > 1) {
 #pragma unroll 1
           for (int s2 = 0; s2 < S - 1; ++s2) {
@@ -523,12 +537,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (bias != nullptr) {
+          // lane l holds bias columns [8l, 8l + 8) of the tile (loaded before the accumulator wait)
+          const int src = unit_col(u) >> 3;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-            load8g(bias + acol0 + j, f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[j + k] += f[k];
+          for (int q = 0; q < 4; ++q) {
+            uint4 bq;
+            bq.x = __shfl_sync(0xffffffffu, bias_v.x, src + q);
+            bq.y = __shfl_sync(0xffffffffu, bias_v.y, src + q);
+            bq.z = __shfl_sync(0xffffffffu, bias_v.z, src + q);
+            bq.w = __shfl_sync(0xffffffffu, bias_v.w, src + q);
+            const float2 b0 = Cvt<T>::unpack2(bq.x), b1 = Cvt<T>::unpack2(bq.y), b2 = Cvt<T>::unpack2(bq.z),
+                         b3 = Cvt<T>::unpack2(bq.w);
+            v[8 * q + 0] += b0.x; v[8 * q + 1] += b0.y; v[8 * q + 2] += b1.x; v[8 * q + 3] += b1.y;
+            v[8 * q + 4] += b2.x; v[8 * q + 5] += b2.y; v[8 * q + 6] += b3.x; v[8 * q + 7] += b3.y;
           }
         }
         if (gb_row != nullptr) {

@@ -29,7 +29,7 @@ SLOTS = 256
 NAMES = {1: "start", 2: "prod.tile_begin", 3: "prod.tile_issued", 10: "mma.tile_begin", 11: "mma.acc_free", 12: "mma.first_stage",
          13: "mma.last_stage", 20: "epi.tile_begin", 21: "epi.acc_ready", 22: "epi.res_wait", 23: "epi.res_ready",
          24: "epi.panel_written", 25: "epi.group_synced", 26: "epi.store_issued+prev_read", 27: "epi.unit_loaded",
-         28: "epi.unit_biased"}
+         28: "epi.unit_biased", 14: "mma.stage_wait_clocks"}
 
 
 def run(M, N, K, geglu=False, residual=True, label="", use_bias=True, verbose=True):
@@ -68,6 +68,10 @@ def run(M, N, K, geglu=False, residual=True, label="", use_bias=True, verbose=Tr
             evs = [(int(x[0]) >> 32, int(x[0]) & 0xffffffff, int(x[1])) for x in rec[cta, r] if int(x[1]) != 0]
             if r == 0 and evs:
                 t0 = evs[0][2]
+            for e, i, t in evs:
+                if e == 14:
+                    agg[(r, "mma.stage_wait_clocks", "(sum over the tile's k-blocks)")].append(i)
+            evs = [x for x in evs if x[0] != 14]
             for (e, i, t), (e2, i2, t2) in zip(evs, evs[1:]):
                 agg[(r, NAMES.get(e, e), NAMES.get(e2, e2))].append(t2 - t)
             if verbose and cta in (0,) and evs and t0 is not None:
