@@ -476,12 +476,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // the MMAs run (lane u takes unit u; a unit is 64 B of bias / one 128 B line of column sums)
       if (lane < my_units) {
         const int pc = tn * BN + unit_col(lane);
+        if (bias != nullptr) prefetch_l1(bias + pc);
         if (gb_row != nullptr) prefetch_l1(gb_row + pc);
         if (EPI == EPI_FULL && p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + pc);
       }
-      // the tile's bias, 8 columns per lane, requested now and consumed (by lane shuffles) after the accumulator wait
-      uint4 bias_v = make_uint4(0u, 0u, 0u, 0u);
-      if (bias != nullptr && lane * 8 < BN) bias_v = *reinterpret_cast<const uint4*>(bias + tn * BN + lane * 8);
 
       if (elected) HB_TRACE(tr, 20, t);
       mbar_wait(&tfull_bar[as], aphase, 0x31);
@@ -495,17 +493,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wsr = p.ws + (((size_t)t * (S - 1)) * CG + rank) * BN * kBM + r_in_tile;
       }
       const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quarter * 32) << 16);
-      // ONE copy of the unit body (not unrolled: instruction-cache footprint, see the header of this kernel); the
-      // accumulator registers are copied out before the next unit's TMEM load is issued into them
-      uint32_t racc[32];
-      tmem_ld_x32(taddr + unit_col(0), racc);
-#pragma unroll 1
-      for (int u = 0; u < my_units; ++u) {
-        tmem_ld_wait();
-        float v[32];
+      uint32_t racc[2][32];
+      tmem_ld_x32(taddr + unit_col(0), racc[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
-        if (u + 1 < my_units) tmem_ld_x32(taddr + unit_col(u + 1), racc);   // overlaps with the math below
+      for (int u = 0; u < kMaxUnits; ++u) {
+        if (u >= my_units) break;
+        tmem_ld_wait();
+        uint32_t(&r)[32] = racc[u & 1];
+        if (u + 1 < my_units) tmem_ld_x32(taddr + unit_col(u + 1), racc[(u + 1) & 1]);   // overlaps with the math below
         const int acol0 = tn * BN + unit_col(u);                   // first accumulator (= weight row) column
         const bool first_of_panel = !geglu || (u & 1) == 0;
         const bool last_of_panel = !geglu || (u & 1) == 1;
@@ -518,6 +513,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 
         if (elected) HB_TRACE(tr, 27, u);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (S > 1) {
 #pragma unroll 1
           for (int s2 = 0; s2 < S - 1; ++s2) {
@@ -537,19 +535,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (bias != nullptr) {
-          // lane l holds bias columns [8l, 8l + 8) of the tile (loaded before the accumulator wait)
-          const int src = unit_col(u) >> 3;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 bq;
-            bq.x = __shfl_sync(0xffffffffu, bias_v.x, src + q);
-            bq.y = __shfl_sync(0xffffffffu, bias_v.y, src + q);
-            bq.z = __shfl_sync(0xffffffffu, bias_v.z, src + q);
-            bq.w = __shfl_sync(0xffffffffu, bias_v.w, src + q);
-            const float2 b0 = Cvt<T>::unpack2(bq.x), b1 = Cvt<T>::unpack2(bq.y), b2 = Cvt<T>::unpack2(bq.z),
-                         b3 = Cvt<T>::unpack2(bq.w);
-            v[8 * q + 0] += b0.x; v[8 * q + 1] += b0.y; v[8 * q + 2] += b1.x; v[8 * q + 3] += b1.y;
-            v[8 * q + 4] += b2.x; v[8 * q + 5] += b2.y; v[8 * q + 6] += b3.x; v[8 * q + 7] += b3.y;
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+            load8g(bias + acol0 + j, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[j + k] += f[k];
           }
         }
         if (gb_row != nullptr) {
@@ -665,7 +656,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const T* rscale = reinterpret_cast<const T*>(p.row_scale);
     const T* resid = reinterpret_cast<const T*>(p.residual);
     T* C = reinterpret_cast<T*>(p.C);
-    const bool geglu = (p.flags & HB_EPI_GEGLU) != 0;
+    const bool geglu = (EPI == EPI_GEGLU) || (EPI == EPI_FULL && (p.flags & HB_EPI_GEGLU) != 0);
     const int chalf = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int it = 0;
     for (int t = first; t < num_tiles; t += stride, ++it) {
@@ -700,7 +691,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_out = geglu ? (p.N >> 1) : p.N;
       // folded LayerNorm of the A rows: v = rstd * (acc - mu * colsum[n])
       float ln_mu = 0.f, ln_rstd = 1.f;
-      if (p.ln_stats != nullptr && row_ok) {
+      if (EPI == EPI_FULL && p.ln_stats != nullptr && row_ok) {
         const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * row);
         ln_mu = st.x / (float)p.K;
         const float var = fmaxf(st.y / (float)p.K - ln_mu * ln_mu, 0.f);
@@ -722,7 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane * 32 < BN / 2 && pc < p.N) {
           if (bias != nullptr) prefetch_l1(bias + pc);
           if (gb_row != nullptr) prefetch_l1(gb_row + pc);
-          if (p.ln_colsum != nullptr) {
+          if (EPI == EPI_FULL && p.ln_colsum != nullptr) {
             prefetch_l1(p.ln_colsum + pc);
             if (pc + 16 < p.N) prefetch_l1(p.ln_colsum + pc + 16);
           }
@@ -763,7 +754,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < CW; ++j) v[j] += __ldcg(w + j * kBM);
             }
           }
-          if (p.ln_stats != nullptr) {
+          if (EPI == EPI_FULL && p.ln_stats != nullptr) {
 #pragma unroll
             for (int j = 0; j < CW; j += 4) {
               if (col0 + j < p.N) {
@@ -797,10 +788,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (p.flags & HB_EPI_SILU) {
+          if (EPI == EPI_FULL && (p.flags & HB_EPI_SILU)) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = silu_f(v[j]);
-          } else if (p.flags & HB_EPI_RELU) {
+          } else if (EPI == EPI_FULL && (p.flags & HB_EPI_RELU)) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
           }
@@ -844,7 +835,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 o4.z = Cvt<T>::pack2(w[4], w[5]);
                 o4.w = Cvt<T>::pack2(w[6], w[7]);
                 *reinterpret_cast<uint4*>(crow + col0 + j) = o4;
-                if (p.stats_out != nullptr) {
+                if (EPI == EPI_FULL && p.stats_out != nullptr) {
                   // statistics of the values as the next LayerNorm will read them (rounded to the storage type)
                   const float2 q0 = Cvt<T>::unpack2(o4.x), q1 = Cvt<T>::unpack2(o4.y), q2 = Cvt<T>::unpack2(o4.z),
                                q3 = Cvt<T>::unpack2(o4.w);
@@ -859,7 +850,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (c + 1 < kChunks) tmem_ld_wait();
       }
-      if (p.stats_out != nullptr && row_ok) {
+      if (EPI == EPI_FULL && p.stats_out != nullptr && row_ok) {
         atomicAdd(p.stats_out + 2 * row, osum);
         atomicAdd(p.stats_out + 2 * row + 1, osq);
       }
@@ -1030,9 +1021,9 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   }
   g_last_splits = d.splits;
   const int grid = (d.splits > 1 ? tiles * d.splits : (tiles < max_ctas ? tiles : max_ctas)) * CG;
-  // instantiated: the run-time-everything epilogue (EPI_FULL) for plain GEMMs and, without TEPI, convs; the
-  // specialised TEPI epilogues for plain GEMMs (PLAIN, GEGLU) and convs (PLAIN)
-  constexpr bool kConvOk = (EPI == EPI_PLAIN) || (EPI == EPI_FULL && !TEPI);
+  // instantiated: GEMM with every epilogue (PLAIN, GEGLU on TEPI kernels, FULL = all options at run time); conv3x3
+  // with PLAIN only (hallo_b200_gemm rejects an activation / LayerNorm fold / GEGLU on a conv)
+  constexpr bool kConvOk = (EPI == EPI_PLAIN);
   auto kern = gemm_tc_kernel<T, BN, STAGES, false, CG, TEPI, EPI>;
   if constexpr (kConvOk) {
     if (q->conv3x3) kern = gemm_tc_kernel<T, BN, STAGES, true, CG, TEPI, EPI>;
@@ -1053,7 +1044,9 @@ template <typename T>
 static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
   const bool force1 = option(OPT_GEMM_1CTA) != 0;     // A/B switch for benchmarking
   const int tiles_m = p->conv3x3 ? 2 : (p->M + kBM - 1) / kBM;
-  if (force1 || tiles_m < 2) return launch_gemm<T, 160, 5, 1>(p, s);
+  // anything beyond bias / group bias / row scale / residual: the epilogue with every option decided at run time
+  const bool plain = (p->flags & (HB_EPI_SILU | HB_EPI_RELU | HB_EPI_GEGLU)) == 0 && p->ln_stats == nullptr && p->stats_out == nullptr;
+  if (force1 || tiles_m < 2) return plain ? launch_gemm<T, 160, 5, 1, false, EPI_PLAIN>(p, s) : launch_gemm<T, 160, 5, 1>(p, s);
   // TMA-store epilogue (TEPI): written after the last GPU session of round 1 -> opt-in until tests/test_gemm_gpu.py
   // has passed with gemm_tepi = 1 on hardware.  Needs whole N tiles and 16-byte aligned C / residual.
   const bool tepi_env = option(OPT_GEMM_TEPI) != 0;
@@ -1069,7 +1062,7 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
       if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true, EPI_PLAIN>(p, s);
       if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true, EPI_PLAIN>(p, s);
       if (p->N % 160 == 0) return launch_gemm<T, 160, 6, 2, true, EPI_PLAIN>(p, s);
-    } else if (!p->conv3x3) {
+    } else {
       if (p->N % 256 == 0) return launch_gemm<T, 256, 5, 2, true>(p, s);
       if (p->N % 192 == 0) return launch_gemm<T, 192, 5, 2, true>(p, s);
       if (p->N % 160 == 0 && !geglu) return launch_gemm<T, 160, 6, 2, true>(p, s);
@@ -1083,15 +1076,16 @@ static int dispatch_gemm(const hb_gemm_params* p, cudaStream_t s) {
     const int pairs = num_sms() / 2;
     const int wide = p->N % 256 == 0 ? 256 : (p->N % 192 == 0 ? 192 : 160);
     if (tiles_m2 * ((p->N + wide - 1) / wide) < pairs) {
-      if (p->N % 128 == 0 && tiles_m2 * (p->N / 128) >= pairs) return launch_gemm<T, 128, 8, 2>(p, s);
-      if (p->N % 64 == 0) return launch_gemm<T, 64, 8, 2>(p, s);
-      if (p->N % 128 == 0) return launch_gemm<T, 128, 8, 2>(p, s);
+      if (p->N % 128 == 0 && tiles_m2 * (p->N / 128) >= pairs)
+        return plain ? launch_gemm<T, 128, 8, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 128, 8, 2>(p, s);
+      if (p->N % 64 == 0) return plain ? launch_gemm<T, 64, 8, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 64, 8, 2>(p, s);
+      if (p->N % 128 == 0) return plain ? launch_gemm<T, 128, 8, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 128, 8, 2>(p, s);
     }
   }
   // widest N tile that divides N: fewer shared-memory bytes per MMA flop (see the header comment)
-  if (p->N % 256 == 0) return launch_gemm<T, 256, 6, 2>(p, s);
-  if (p->N % 192 == 0) return launch_gemm<T, 192, 7, 2>(p, s);
-  return launch_gemm<T, 160, 7, 2>(p, s);
+  if (p->N % 256 == 0) return plain ? launch_gemm<T, 256, 6, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 256, 6, 2>(p, s);
+  if (p->N % 192 == 0) return plain ? launch_gemm<T, 192, 7, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 192, 7, 2>(p, s);
+  return plain ? launch_gemm<T, 160, 7, 2, false, EPI_PLAIN>(p, s) : launch_gemm<T, 160, 7, 2>(p, s);
 }
 
 }  // namespace hb
@@ -1122,6 +1116,8 @@ extern "C" int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream) {
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: leading dims / N must be multiples of 8");
   if ((p->ln_stats != nullptr) != (p->ln_colsum != nullptr) || (p->ln_stats != nullptr && (p->conv3x3 || p->N % 4 != 0)))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: ln_stats and ln_colsum go together (plain GEMM only)");
+  if (p->conv3x3 && ((p->flags & (HB_EPI_SILU | HB_EPI_RELU | HB_EPI_GEGLU)) != 0 || p->stats_out != nullptr))
+    return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: conv3x3 takes bias / group bias / row scale / residual only");
   if (p->stats_out != nullptr && (p->flags & HB_EPI_GEGLU))
     return fail(HB_ERR_BAD_SHAPE, "hallo_b200_gemm: stats_out is not defined for the GEGLU epilogue");
   if (p->scatter != nullptr && (p->residual != nullptr || p->conv3x3 || p->scatter->seg <= 0 ||

@@ -90,6 +90,7 @@ int hallo_b200_get_option(const char* name);
  *   conv3x3 == 2: stride-2 conv (Downsample3D, resnet.py:232-252).  A holds the 4 phase planes
  *        written by hallo_b200_phase_split: [4*img_n, img_h, img_w, Cin] where img_h/img_w are
  *        the OUTPUT height/width; M = img_n*img_h*img_w.
+ *        A conv takes bias / group_bias / row_scale / residual only (no activation, GEGLU, LayerNorm fold, stats_out).
  *   epilogue, in this order (each optional):
  *        v  = acc + bias[col] + group_bias[row / rows_per_group][col]
  *        v  = v_even * gelu_erf(v_odd)           (HB_EPI_GEGLU: W rows interleaved value/gate,
