@@ -876,6 +876,23 @@ constexpr long long kSplitKCounterBytes = 8192;     // head of the split-K works
 constexpr int kSplitKMinBlocks = 32;                // shortest K loop (64-wide k-blocks) that is split
 static int g_last_splits = 1;                       // split factor of the most recent launch (tests / diagnostics)
 
+// Split factor of a launch of `tiles` (pairs of) tiles on `max_ctas` (pairs of) SMs; pure host arithmetic, also exported
+// as hallo_b200_gemm_choose_splits for the CPU tests.  1 = unsplit.
+static int choose_splits(int tiles, int max_ctas, int kblocks, int cg, int bn, long long workspace_bytes, int splitk_opt) {
+  const int min_blocks = splitk_opt > 1 ? splitk_opt : kSplitKMinBlocks;
+  if (splitk_opt == 0 || workspace_bytes <= kSplitKCounterBytes || tiles <= 0 || tiles * 2 > max_ctas || kblocks < min_blocks ||
+      (long long)tiles * cg * 8 * (long long)sizeof(int) > kSplitKCounterBytes)
+    return 1;
+  int S = (int)(sqrtf((float)kblocks / 4.0f) + 0.5f);
+  if (S > max_ctas / tiles) S = max_ctas / tiles;
+  if (S > 16) S = 16;
+  const long long tile_bytes = (long long)cg * bn * kBM * (long long)sizeof(float);
+  const long long room = (workspace_bytes - kSplitKCounterBytes) / tile_bytes;      // partial tiles that fit
+  while (S > 1 && (long long)tiles * (S - 1) > room) --S;
+  while (S > 1 && (S - 1) * ((kblocks + S - 1) / S) >= kblocks) --S;                // no empty split
+  return S > 1 ? S : 1;
+}
+
 // pick the NHWC box (box_w, box_h, box_n), box_w*box_h*box_n == 128, that covers the image batch with the
 // fewest tiles; boxes may overhang (TMA zero-fills, the epilogue masks), so any image size works.
 static void pick_conv_box(int n, int h, int w, int* bw, int* bh, int* bn) {
@@ -1000,24 +1017,11 @@ static int launch_gemm(const hb_gemm_params* q, cudaStream_t stream) {
   // (128 x BN fp32) back, so the per-CTA traffic is smallest near S = sqrt(kblocks / 4).  The hand-over (partial
   // store, fence, counter, read-back) costs ~4 us, which a K loop below kSplitKMinBlocks k-blocks does not win back
   // (profiles/r2_kbench_latency_splitk.log); an option value > 1 overrides that threshold (A/B runs).
-  d.splits = 1;
-  const int kblocks = q->K / kBK;
-  const int splitk_opt = option(OPT_GEMM_SPLITK);
-  const int min_blocks = splitk_opt > 1 ? splitk_opt : kSplitKMinBlocks;
-  if (splitk_opt != 0 && q->workspace != nullptr && tiles * 2 <= max_ctas && kblocks >= min_blocks &&
-      (long long)tiles * CG * 8 * (long long)sizeof(int) <= kSplitKCounterBytes) {
-    int S = (int)(sqrtf((float)kblocks / 4.0f) + 0.5f);
-    if (S > max_ctas / tiles) S = max_ctas / tiles;
-    if (S > 16) S = 16;
-    const long long tile_bytes = (long long)CG * BN * kBM * (long long)sizeof(float);
-    const long long room = (q->workspace_bytes - kSplitKCounterBytes) / tile_bytes;      // partial tiles that fit
-    while (S > 1 && (long long)tiles * (S - 1) > room) --S;
-    while (S > 1 && (S - 1) * ((kblocks + S - 1) / S) >= kblocks) --S;                  // no empty split
-    if (S > 1) {
-      d.splits = S;
-      d.cnt = reinterpret_cast<int*>(q->workspace);
-      d.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->workspace) + kSplitKCounterBytes);
-    }
+  d.splits = choose_splits(tiles, max_ctas, q->K / kBK, CG, BN, q->workspace != nullptr ? q->workspace_bytes : 0,
+                           option(OPT_GEMM_SPLITK));
+  if (d.splits > 1) {
+    d.cnt = reinterpret_cast<int*>(q->workspace);
+    d.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->workspace) + kSplitKCounterBytes);
   }
   g_last_splits = d.splits;
   const int grid = (d.splits > 1 ? tiles * d.splits : (tiles < max_ctas ? tiles : max_ctas)) * CG;
@@ -1096,6 +1100,10 @@ extern "C" long long hallo_b200_gemm_workspace_bytes(void) {
 }
 
 extern "C" int hallo_b200_gemm_last_splits(void) { return hb::g_last_splits; }
+extern "C" int hallo_b200_gemm_choose_splits(int tiles, int sm_units, int K, int cta_group, int bn, long long workspace_bytes,
+                                             int option_value) {
+  return hb::choose_splits(tiles, sm_units, K / hb::kBK, cta_group, bn, workspace_bytes, option_value);
+}
 
 #ifdef HB_GEMM_TRACE
 // tools/gemm_trace.py only: buffer of gridDim.x * 4 recorders * 256 records * 2 int64 (NULL = off)

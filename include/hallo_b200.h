@@ -166,6 +166,11 @@ int hallo_b200_gemm(const hb_gemm_params* p, hb_stream_t stream);
 long long hallo_b200_gemm_workspace_bytes(void);
 /* split factor the most recent hallo_b200_gemm call of this process used (1 = unsplit): tests / diagnostics */
 int hallo_b200_gemm_last_splits(void);
+/* The split-K decision itself (host arithmetic, no device needed): `tiles` output tiles (CTA pairs count as one) on
+ * `sm_units` SMs (pairs: SMs / 2), reduction length K, tile width bn, the caller's workspace size and the value of option
+ * "gemm_splitk" (0 = off, 1 = default threshold K >= 2048, n > 1 = K >= 64 n).  Returns the split factor, 1 = unsplit. */
+int hallo_b200_gemm_choose_splits(int tiles, int sm_units, int K, int cta_group, int bn, long long workspace_bytes,
+                                  int option_value);
 
 /* ------------------------------------------------------------------------------------------
  * hallo_b200_attention -- fused softmax(Q K^T / sqrt(d)) V, tcgen05 + TMEM, flash-style.

@@ -365,3 +365,36 @@ def test_from_pretrained_2d_on_a_synthetic_checkpoint(tmp_path):
         (tmp_path / "mm.bad").write_bytes(b"x")
         UNet3DConditionModel.from_pretrained_2d(str(base), str(tmp_path / "mm.bad"), subfolder="unet",
                                                 unet_additional_kwargs=dict(HALLO_UNET_KWARGS), use_landmark=False)
+
+
+def test_split_k_decision_is_host_arithmetic():
+    """hallo_b200_gemm_choose_splits (include/hallo_b200.h): which launches divide their K loop, and how far.  Pure host
+    arithmetic of the library, callable without a device."""
+    import __graft_entry__ as g
+    g.build()
+    from hallo_b200 import lib
+    h = lib.load()
+    f = h.hallo_b200_gemm_choose_splits
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]
+    ws = int(h.hallo_b200_gemm_workspace_bytes())
+    pairs = 74
+    # level-3 conv of one rank of an 8-way shard: 5 tiles, K = 9 * 1280 -> 180 k-blocks -> ~sqrt(180 / 4) = 7 splits
+    assert f(5, pairs, 11520, 2, 256, ws, 1) == 7
+    # the FF-out GEMM of the same rank (K = 5120): 4 splits; the K = 1280 linears stay whole at the default threshold ...
+    assert f(5, pairs, 5120, 2, 256, ws, 1) == 4
+    assert f(5, pairs, 1280, 2, 256, ws, 1) == 1
+    # ... and split in two when the option lowers the threshold to 16 k-blocks (the GPU tests use that)
+    assert f(5, pairs, 1280, 2, 256, ws, 16) == 2
+    # never more CTAs than SM pairs, never when the tiles already cover half of them, never without a workspace
+    assert f(20, pairs, 11520, 2, 256, ws, 1) == 3
+    assert f(40, pairs, 11520, 2, 256, ws, 1) == 1
+    assert f(5, pairs, 11520, 2, 256, 0, 1) == 1
+    assert f(5, pairs, 11520, 2, 256, ws, 0) == 1
+    # a workspace with room for 8 partial tiles (pairs of 128 x 256 fp32) caps the split count: 5 tiles * (S - 1) <= 8
+    small = 8192 + 8 * 2 * 256 * 128 * 4
+    assert f(5, pairs, 11520, 2, 256, small, 1) == 2
+    # every split owns at least one k-block: 33 k-blocks in 3 splits of 11 is fine, S is reduced where the last would be empty
+    for kb in range(32, 400, 7):
+        S = f(2, pairs, kb * 64, 2, 256, ws, 1)
+        per = -(-kb // S)
+        assert S >= 1 and (S - 1) * per < kb, (kb, S)
