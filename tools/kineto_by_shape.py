@@ -1,3 +1,10 @@
+"""Match the in-graph kernel durations of `bench.py --kineto FILE` to op shapes (read here, no GPU needed).
+
+`FILE.seq` lists the kernels of one graph replay in launch order (CUPTI duration, grid, name); `FILE.ops` lists the
+hallo_b200.ops calls of one eager step in the same order.  Every op launches a known set of kernels (a GroupNorm is one
+fused launch or three; everything else one), so walking both lists in step gives the warm, in-graph time of every op
+shape -- the table DESIGN.md 4.4 quotes.
+    python tools/kineto_by_shape.py gpurun_out/r2t_kineto_n1.txt [rows]"""
 import re,collections,sys
 def load(prefix):
     seq=[l.rstrip('\n') for l in open(prefix+'.seq')]
